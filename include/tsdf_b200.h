@@ -1,0 +1,176 @@
+/*
+ * tsdf_b200.h — C-ABI of the B200-native TSDF integrate + raycast hot path.
+ *
+ * The reference (Scoobadood/TSDF) has no FFI of its own: its boundary is the C++ class
+ * surface kinfu.cpp compiles against (src/include/TSDFVolume.hpp, Camera.hpp,
+ * Raycaster.hpp, GPURaycaster.hpp).  This header is the seam *under* those classes:
+ * level 1 mirrors the reference's kernel launches one to one (raw device pointers + POD
+ * parameters, what TSDFVolume.cu / GPURaycaster.cu pass to their __global__ functions);
+ * level 2 mirrors the class methods (opaque handles, HOST buffers, synchronous like the
+ * reference) and is what the drop-in C++ classes in tsdf_b200/include forward to.
+ *
+ * Conventions: every function returns 0 on success, a cudaError_t value (>0) for CUDA
+ * failures, or a negative TSDF_B200_E* code for argument errors.  Nothing here calls
+ * exit().  Matrices are COLUMN-major float arrays — the storage of Eigen::Matrix4f /
+ * Matrix3f::data() and of the reference's Mat44/Mat33 (src/include/cuda_utilities.hpp:12-23).
+ * Volumes are x-fastest: index = x + y*nx + z*nx*ny (src/include/TSDFVolume.hpp:165-167).
+ * `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).
+ *
+ * All citations are relative to the reference tree's src/ directory.
+ */
+#ifndef TSDF_B200_H
+#define TSDF_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TSDF_B200_EINVAL (-1)   /* bad argument (null pointer, zero size, unsupported dimension) */
+#define TSDF_B200_ENOMEM (-2)
+#define TSDF_B200_EIO    (-3)
+#define TSDF_B200_ESTATE (-4)
+
+/* Longest ray: samples k = 0..4401 (RayCaster/GPURaycaster.cu:369 `count++ > 4400`). */
+#define TSDF_B200_MAX_SAMPLES 4402
+/* Floats in a ray-parameter table (tsdf_b200_ray_table). */
+#define TSDF_B200_RAY_TABLE_LEN 4416
+/* Edge of an occupancy brick in voxels (empty-space skipping grid). */
+#define TSDF_B200_BRICK 8
+
+const char *tsdf_b200_version(void);
+/* Text for any return code of this library (cudaGetErrorString for positive codes). */
+const char *tsdf_b200_strerror(int code);
+
+/* ------------------------------------------------------------------------------------
+ * Level 1 — kernel launches.  All pointers are DEVICE pointers unless marked host.
+ * ---------------------------------------------------------------------------------- */
+
+/* Volume constants as TSDFVolume::set_size derives them (TSDF/TSDFVolume.cu:686-693):
+ * voxel = physical / size (element-wise), trunc = 1.1f * |voxel|.  Host-only arithmetic. */
+int tsdf_b200_volume_params(uint32_t nx, uint32_t ny, uint32_t nz, const float physical[3],
+                            float voxel_out[3], float *trunc_out);
+
+/* Replaces set_memory_to_value x2 in TSDFVolume::clear (TSDF/TSDFVolume.cu:797-832):
+ * weight <- 0, dist <- trunc.  d_occ (optional, tsdf_b200_occupancy_bytes() long) <- 0. */
+int tsdf_b200_clear(float *d_dist, float *d_weight, uint32_t nx, uint32_t ny, uint32_t nz,
+                    float trunc, uint8_t *d_occ, void *stream);
+
+/* Replaces initialise_deformation (TSDF/TSDFVolume.cu:768-794): node = {((v+0.5)*voxel)+
+ * grid_offset, 0}; d_deform holds 6 floats per voxel (TSDFVolume::DeformationNode).     */
+int tsdf_b200_init_deformation(float *d_deform, uint32_t nx, uint32_t ny, uint32_t nz,
+                               const float voxel[3], const float grid_offset[3], void *stream);
+
+/* Replaces integrate_kernel (TSDF/TSDFVolume.cu:308-392) for planes z in [z_begin, z_end).
+ * d_deform == NULL selects the analytic identity grid: translation = ((v+0.5)*voxel) +
+ * offset_at_clear, bit-identical to reading the array clear() wrote, without the 24 B/voxel
+ * read.  d_occ (optional): occupancy bricks are marked for every voxel whose new distance
+ * leaves the "certainly positive" band.  d_n_updated (optional): incremented by the number
+ * of voxels rewritten (device counter, unsigned long long).                             */
+int tsdf_b200_integrate(float *d_dist, float *d_weight, const float *d_deform,
+                        uint32_t nx, uint32_t ny, uint32_t nz, const float voxel[3],
+                        const float offset_at_clear[3], const float offset[3], float trunc,
+                        const float inv_pose[16], const float k[9], const float kinv[9],
+                        uint32_t width, uint32_t height, const uint16_t *d_depth,
+                        uint32_t z_begin, uint32_t z_end, uint8_t *d_occ,
+                        unsigned long long *d_n_updated, void *stream);
+
+/* Size in bytes of the occupancy grid for a volume (one byte per 8^3 brick). */
+size_t tsdf_b200_occupancy_bytes(uint32_t nx, uint32_t ny, uint32_t nz);
+
+/* Recompute the occupancy grid from scratch (after set_distance_data / file load). */
+int tsdf_b200_occupancy_rebuild(const float *d_dist, uint32_t nx, uint32_t ny, uint32_t nz,
+                                float trunc, uint8_t *d_occ, void *stream);
+
+/* Ray parameter table t_k: t_0 = 0, t_{k+1} = t_k + step, step = (float)(trunc * 0.05)
+ * (RayCaster/GPURaycaster.cu:316,324,360) — identical for every ray of a volume.
+ * d_table holds TSDF_B200_RAY_TABLE_LEN floats.                                         */
+int tsdf_b200_ray_table(float trunc, float *d_table, void *stream);
+
+/* Replaces process_ray (RayCaster/GPURaycaster.cu:265-377).  d_vertices: 3 floats per
+ * pixel, index y*width+x, NaN^3 for rays without a hit.  d_khit (optional): sample index
+ * of the hit, -1 otherwise.  d_occ (optional): occupancy grid enabling exact empty-space
+ * skipping.  d_n_samples (optional): incremented by trilinear samples actually evaluated. */
+int tsdf_b200_raycast(const float *d_dist, uint32_t nx, uint32_t ny, uint32_t nz,
+                      const float voxel[3], const float space_min[3], const float space_max[3],
+                      float trunc, const float origin[3], const float rot[9], const float kinv[9],
+                      uint32_t width, uint32_t height, const float *d_table,
+                      const uint8_t *d_occ, float *d_vertices, int32_t *d_khit,
+                      unsigned long long *d_n_samples, void *stream);
+
+/* tsdf_b200_raycast with the division by the voxel size done as a 3-instruction reciprocal
+ * sequence when fastdiv != 0.  Pass 1 only after tsdf_b200_selftest_division() returned zero
+ * mismatches for voxel[0], voxel[1] and voxel[2]; results are then bit-identical.        */
+int tsdf_b200_raycast_ex(const float *d_dist, uint32_t nx, uint32_t ny, uint32_t nz,
+                         const float voxel[3], const float space_min[3], const float space_max[3],
+                         float trunc, const float origin[3], const float rot[9], const float kinv[9],
+                         uint32_t width, uint32_t height, const float *d_table,
+                         const uint8_t *d_occ, float *d_vertices, int32_t *d_khit,
+                         unsigned long long *d_n_samples, int fastdiv, void *stream);
+
+/* Replaces the compute_normals kernel (RayCaster/GPURaycaster.cu:393-427). */
+int tsdf_b200_normals(uint32_t width, uint32_t height, const float *d_vertices,
+                      float *d_normals, void *stream);
+
+/* Exhaustive check (every numerator bit pattern with 2^-100 <= |a| <= 2^100, and +-0) that the
+ * 3-instruction reciprocal division used by the raycast kernel equals IEEE a/divisor.  *mismatches is a
+ * host pointer.  The level-2 volume runs this once per voxel size and falls back to
+ * IEEE division in the kernel when it is not zero.                                      */
+int tsdf_b200_selftest_division(float divisor, unsigned long long *mismatches);
+
+/* ------------------------------------------------------------------------------------
+ * Level 2 — object API with HOST buffers (what kinfu.cpp reaches through the classes).
+ * ---------------------------------------------------------------------------------- */
+typedef struct tsdf_b200_volume tsdf_b200_volume;
+
+/* TSDFVolume(UInt3, Float3) / set_size (TSDF/TSDFVolume.cu:430-437, 679-722). */
+int tsdf_b200_volume_create(uint32_t nx, uint32_t ny, uint32_t nz, float px, float py, float pz,
+                            tsdf_b200_volume **out);
+/* TSDFVolume(const std::string&) load constructor (TSDF/TSDFVolume.cu:463-664). */
+int tsdf_b200_volume_load(const char *path, tsdf_b200_volume **out);
+void tsdf_b200_volume_destroy(tsdf_b200_volume *v);
+
+int tsdf_b200_volume_get(const tsdf_b200_volume *v, uint32_t size[3], float physical[3],
+                         float voxel[3], float offset[3], float *trunc, float *max_weight);
+/* TSDFVolume::offset(ox,oy,oz) (include/TSDFVolume.hpp:144-148). */
+int tsdf_b200_volume_set_offset(tsdf_b200_volume *v, float ox, float oy, float oz);
+/* TSDFVolume::clear (TSDF/TSDFVolume.cu:812-845). */
+int tsdf_b200_volume_clear(tsdf_b200_volume *v);
+/* distance_data()/weight_data(): raw device pointers, valid on the default stream. */
+const float *tsdf_b200_volume_distance_data(const tsdf_b200_volume *v);
+const float *tsdf_b200_volume_weight_data(const tsdf_b200_volume *v);
+/* deformation(): materialises the 24 B/voxel node array on first use. */
+float *tsdf_b200_volume_deformation(tsdf_b200_volume *v);
+/* set_distance_data / set_weight_data / set_deformation (TSDF/TSDFVolume.cu:729-755). */
+int tsdf_b200_volume_set_distance_data(tsdf_b200_volume *v, const float *host);
+int tsdf_b200_volume_set_weight_data(tsdf_b200_volume *v, const float *host);
+int tsdf_b200_volume_set_deformation(tsdf_b200_volume *v, const float *host_nodes);
+/* Device -> host copies for tests and tools. */
+int tsdf_b200_volume_read(const tsdf_b200_volume *v, float *host_dist, float *host_weight);
+
+/* TSDFVolume::integrate (TSDF/TSDFVolume.cu:861-902): host depth map, camera matrices as
+ * Camera::inverse_pose()/k()/kinv() .data().  Synchronous.                              */
+int tsdf_b200_volume_integrate(tsdf_b200_volume *v, const uint16_t *host_depth, uint32_t width,
+                               uint32_t height, const float inv_pose[16], const float k[9],
+                               const float kinv[9]);
+/* TSDFVolume::raycast -> GPURaycaster::raycast (TSDF/TSDFVolume.cu:1054-1058,
+ * RayCaster/GPURaycaster.cu:519-547): pose = Camera::pose().data().  host_vertices /
+ * host_normals receive 3*width*height floats each.  Synchronous.                        */
+int tsdf_b200_volume_raycast(const tsdf_b200_volume *v, uint32_t width, uint32_t height,
+                             const float pose[16], const float kinv[9], float *host_vertices,
+                             float *host_normals);
+/* TSDFVolume::save_to_file (TSDF/TSDFVolume.cu:911-1027), byte-compatible format. */
+int tsdf_b200_volume_save(const tsdf_b200_volume *v, const char *path);
+
+/* Counters of the last integrate / raycast (voxels rewritten, samples evaluated). */
+int tsdf_b200_volume_stats(const tsdf_b200_volume *v, unsigned long long *n_updated,
+                           unsigned long long *n_samples);
+/* 0 disables / 1 enables empty-space skipping in volume_raycast (default 1). */
+int tsdf_b200_volume_set_skipping(tsdf_b200_volume *v, int enabled);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TSDF_B200_H */

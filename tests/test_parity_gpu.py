@@ -1,0 +1,425 @@
+"""GPU parity tests: the sm_100a kernels, called through the C-ABI, against the CPU oracle.
+
+Bar: bit-exact distances, weights, vertices, normals, hit sample index k and hit voxel.
+The north star asks for <= 1e-4 relative on SDF values; bit equality is the stronger statement and is
+what is asserted.  Oracle-sized cases finish in seconds on the host; full-size cases (512^3) are
+covered by size-independent properties in test_fullsize_gpu.py.
+"""
+import numpy as np
+import pytest
+
+from helpers import assert_bits_equal, random_rigid_pose, random_depth
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def G(built):
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    import gpu_util
+    return gpu_util
+
+
+def quarter_intrinsics(cam, s):
+    k = cam.k.copy()
+    k[:2] *= s
+    kinv = np.linalg.inv(k.astype(np.float64)).astype(np.float32)
+    return k, kinv
+
+
+def sphere_sdf(n, physical, trunc, centre, radius):
+    """create_sphere_in_TSDF of the reference (TestHelpers.cpp:18-61): analytic SDF clamped to +-trunc."""
+    vs = np.asarray(physical, np.float64) / np.asarray(n)
+    z, y, x = np.meshgrid(*(np.arange(m) + 0.5 for m in (n[2], n[1], n[0])), indexing="ij")
+    d = np.sqrt((x * vs[0] - centre[0]) ** 2 + (y * vs[1] - centre[1]) ** 2 + (z * vs[2] - centre[2]) ** 2) - radius
+    return np.clip(d, -trunc, trunc).astype(np.float32).reshape(-1)
+
+
+# ----------------------------------------------------------------------------------- integrate
+@pytest.mark.parametrize("n", [(64, 64, 64), (128, 128, 128), (36, 20, 28), (33, 17, 9), (4, 4, 4), (1, 1, 1), (130, 3, 5)])
+def test_integrate_matches_oracle(G, n):
+    from oracle import oracle
+    from tsdf_b200 import scenes
+    rng = np.random.default_rng(sum(n))
+    dv = G.DeviceVolume(n, (3000, 3000, 3000))
+    ov = oracle.OracleVolume(n, (3000, 3000, 3000))
+    for f in range(3):
+        cam = scenes.orbit_camera(f * 5 + 1, 16)
+        k, kinv = quarter_intrinsics(cam, 0.5)
+        depth = scenes.render_depth(cam, 320, 240)
+        nu = dv.integrate(depth, cam.inv_pose, k, kinv)
+        no = ov.integrate(depth, cam.inv_pose, k, kinv)
+        assert nu == no
+    assert_bits_equal(dv.dist.cpu().numpy(), ov.dist, "dist")
+    assert_bits_equal(dv.weight.cpu().numpy(), ov.weight, "weight")
+
+
+def test_integrate_config1_fixed_pose(G):
+    """BASELINE config 1 geometry: 128^3, 640x480, fixed pose, identical frames (3 of the 10)."""
+    from oracle import oracle
+    from tsdf_b200 import scenes
+    cam = scenes.fixed_pose_camera()
+    depth = scenes.render_depth(cam)
+    dv = G.DeviceVolume((128,) * 3, (3000,) * 3)
+    ov = oracle.OracleVolume((128,) * 3, (3000,) * 3)
+    for _ in range(3):
+        assert dv.integrate(depth, cam.inv_pose, cam.k, cam.kinv) == ov.integrate(depth, cam.inv_pose, cam.k, cam.kinv)
+    assert_bits_equal(dv.dist.cpu().numpy(), ov.dist, "dist")
+    assert_bits_equal(dv.weight.cpu().numpy(), ov.weight, "weight")
+
+
+def test_integrate_random_poses_and_depth(G):
+    from oracle import oracle
+    rng = np.random.default_rng(1234)
+    n = (72, 56, 40)
+    dv = G.DeviceVolume(n, (2500, 3000, 2000), offset=(100.0, -50.0, 25.5))
+    ov = oracle.OracleVolume(n, (2500, 3000, 2000))
+    ov.offset[:] = (100.0, -50.0, 25.5); ov.clear()
+    for f in range(6):
+        cam = random_rigid_pose(rng, centre=(1350, 1450, 1025))
+        k, kinv = quarter_intrinsics(cam, 0.25)
+        depth = random_depth(rng, 160, 120)
+        assert dv.integrate(depth, cam.inv_pose, k, kinv) == ov.integrate(depth, cam.inv_pose, k, kinv)
+    assert_bits_equal(dv.dist.cpu().numpy(), ov.dist, "dist")
+    assert_bits_equal(dv.weight.cpu().numpy(), ov.weight, "weight")
+
+
+def test_integrate_general_matrices(G):
+    """Non-affine inverse pose (w != 1), skewed K and a K^-1 whose third row is not (0,0,1), camera
+    inside the volume (voxels behind the camera still project, TSDFVolume.cu has no cull)."""
+    from oracle import oracle
+    rng = np.random.default_rng(99)
+    n = (40, 40, 40)
+    dv = G.DeviceVolume(n, (3000,) * 3)
+    ov = oracle.OracleVolume(n, (3000,) * 3)
+    for f in range(4):
+        cam = random_rigid_pose(rng, radius=(100.0, 1400.0))
+        ip = cam.inv_pose.copy()
+        ip[3] = (1e-5, -2e-5, 3e-5, 1.01)
+        k = cam.k.copy(); k[:2] *= 0.25; k[0, 1] = 0.7; k[2] = (1e-4, -1e-4, 1.0)
+        kinv = np.linalg.inv(k.astype(np.float64)).astype(np.float32)
+        depth = random_depth(rng, 160, 120, lo=1, hi=3000, holes=0.3)
+        assert dv.integrate(depth, ip, k, kinv) == ov.integrate(depth, ip, k, kinv)
+    assert_bits_equal(dv.dist.cpu().numpy(), ov.dist, "dist")
+    assert_bits_equal(dv.weight.cpu().numpy(), ov.weight, "weight")
+
+
+def test_integrate_degenerate_inputs(G):
+    """All-zero depth (nothing fused), camera plane cutting the volume (img.z = 0 -> NaN/inf pixel
+    coordinates; NaN converts to pixel 0 on the GPU), maximum depth value."""
+    from oracle import oracle
+    from tsdf_b200 import scenes
+    n = (32, 32, 32)
+    dv = G.DeviceVolume(n, (3000,) * 3)
+    ov = oracle.OracleVolume(n, (3000,) * 3)
+    cam = scenes.PinholeCamera()
+    cam.move_to(1500.0, 1500.0, 1500.0 + 0.5 * 93.75)      # camera z exactly on a voxel-centre plane
+    k, kinv = quarter_intrinsics(cam, 0.25)
+    zero = np.zeros((120, 160), np.uint16)
+    assert dv.integrate(zero, cam.inv_pose, k, kinv) == 0 == ov.integrate(zero, cam.inv_pose, k, kinv)
+    full = np.full((120, 160), 65535, np.uint16)
+    assert dv.integrate(full, cam.inv_pose, k, kinv) == ov.integrate(full, cam.inv_pose, k, kinv)
+    # principal point at pixel (0,0) so the NaN -> 0 conversion lands inside the image
+    k2 = k.copy(); k2[0, 2] = 0; k2[1, 2] = 0
+    kinv2 = np.linalg.inv(k2.astype(np.float64)).astype(np.float32)
+    cam.move_to(1500.0 + 0.5 * 93.75, 1500.0 + 0.5 * 93.75, 1500.0 + 0.5 * 93.75)
+    d3 = np.full((120, 160), 1000, np.uint16)
+    assert dv.integrate(d3, cam.inv_pose, k2, kinv2) == ov.integrate(d3, cam.inv_pose, k2, kinv2)
+    assert_bits_equal(dv.dist.cpu().numpy(), ov.dist, "dist")
+    assert_bits_equal(dv.weight.cpu().numpy(), ov.weight, "weight")
+
+
+def test_integrate_deformation_array_path(G):
+    """Stored deformation nodes (the reference's only path) == analytic grid, then a perturbed field."""
+    import torch
+    from oracle import oracle
+    from tsdf_b200 import scenes
+    n = (48, 40, 32)
+    cam = scenes.orbit_camera(2, 16)
+    k, kinv = quarter_intrinsics(cam, 0.25)
+    depth = scenes.render_depth(cam, 160, 120)
+    a = G.DeviceVolume(n, (3000,) * 3, with_deformation=True)
+    b = G.DeviceVolume(n, (3000,) * 3)
+    ov = oracle.OracleVolume(n, (3000,) * 3, with_deformation=True)
+    assert_bits_equal(a.deform.cpu().numpy(), ov.deform, "deformation grid")
+    assert a.integrate(depth, cam.inv_pose, k, kinv) == b.integrate(depth, cam.inv_pose, k, kinv)
+    ov.integrate(depth, cam.inv_pose, k, kinv)
+    assert_bits_equal(a.dist.cpu().numpy(), b.dist.cpu().numpy(), "dist array-vs-analytic")
+    assert_bits_equal(a.dist.cpu().numpy(), ov.dist, "dist")
+    rng = np.random.default_rng(5)
+    ov.deform[:] = ov.deform + rng.normal(0, 20, ov.deform.size).astype(np.float32)
+    a.deform.copy_(torch.from_numpy(ov.deform))
+    assert a.integrate(depth, cam.inv_pose, k, kinv) == ov.integrate(depth, cam.inv_pose, k, kinv)
+    assert_bits_equal(a.dist.cpu().numpy(), ov.dist, "dist deformed")
+    assert_bits_equal(a.weight.cpu().numpy(), ov.weight, "weight deformed")
+
+
+def test_integrate_z_ranges_compose(G):
+    """Z-slab decomposition (the multi-GPU sharding unit): slabs fused separately == whole volume."""
+    from tsdf_b200 import scenes
+    n = (64, 48, 40)
+    cam = scenes.orbit_camera(3, 16)
+    k, kinv = quarter_intrinsics(cam, 0.25)
+    depth = scenes.render_depth(cam, 160, 120)
+    whole = G.DeviceVolume(n, (3000,) * 3)
+    parts = G.DeviceVolume(n, (3000,) * 3)
+    total = whole.integrate(depth, cam.inv_pose, k, kinv)
+    got = sum(parts.integrate(depth, cam.inv_pose, k, kinv, z0, z1) for z0, z1 in ((0, 13), (13, 14), (14, 40)))
+    assert got == total
+    assert_bits_equal(whole.dist.cpu().numpy(), parts.dist.cpu().numpy(), "dist")
+    assert_bits_equal(whole.weight.cpu().numpy(), parts.weight.cpu().numpy(), "weight")
+
+
+def test_clear_and_golden_fixture(G):
+    import hashlib, json, os
+    g = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "t_100_2000_50.json")))
+    dv = G.DeviceVolume(g["size"], g["physical"], with_deformation=True)
+    sha = lambda t: hashlib.sha256(t.cpu().numpy().tobytes()).hexdigest()
+    assert int(np.float32(dv.trunc).view(np.uint32)) == g["trunc_bits"]
+    assert sha(dv.dist) == g["dist_sha256"] and sha(dv.weight) == g["weight_sha256"] and sha(dv.deform) == g["deform_sha256"]
+
+
+# ------------------------------------------------------------------------------------- raycast
+def check_raycast(G, dv, ov, w, h, pose, kinv, what):
+    from oracle import oracle
+    Vo, No, ko, so = ov.raycast(w, h, pose, kinv)
+    results = {}
+    for skip in (False, True):
+        for fastdiv in (False, True):
+            V, N, kh, ns = dv.raycast(w, h, pose, kinv, skip=skip, fastdiv=fastdiv)
+            tag = f"{what} skip={skip} fastdiv={fastdiv}"
+            assert np.array_equal(kh, ko), tag + ": hit sample index k differs"
+            assert_bits_equal(V, Vo, tag + ": vertices")
+            assert_bits_equal(N, No, tag + ": normals")
+            hv = oracle.hit_voxels(V, ov.offset, ov.voxel, ov.size[0], ov.size[1])
+            ho = oracle.hit_voxels(Vo, ov.offset, ov.voxel, ov.size[0], ov.size[1])
+            assert np.array_equal(hv, ho), tag + ": hit voxel index differs"
+            if not skip:
+                assert ns == so, tag + ": sample count differs from the reference march"
+            else:
+                assert ns <= so
+            results[(skip, fastdiv)] = ns
+    return results, int((ko >= 0).sum()), so
+
+
+def test_raycast_sphere_reference_poses(G):
+    """The two live camera placements of Test_TSDF_RayCast.cpp (:416-431, :568-581): sphere SDF in a
+    volume, camera at (450,150,150)->(150,150,150) and (-150,150,450)->(150,150,150), scaled x10."""
+    from oracle import oracle
+    from tsdf_b200 import scenes
+    n = (96, 96, 96)
+    dv = G.DeviceVolume(n, (3000,) * 3)
+    ov = oracle.OracleVolume(n, (3000,) * 3)
+    sdf = sphere_sdf(n, (3000,) * 3, ov.trunc, (1500, 1500, 1500), 800)
+    ov.dist[:] = sdf
+    dv.upload_dist(sdf)
+    for pos in ((4500, 1500, 1500), (-1500, 1500, 4500), (1500, 1500, -2500), (1500, 5200, 1500)):
+        cam = scenes.PinholeCamera()
+        cam.move_to(*pos)
+        cam.look_at(1500, 1500, 1500)
+        k, kinv = quarter_intrinsics(cam, 0.5)
+        res, hits, so = check_raycast(G, dv, ov, 320, 240, cam.pose, kinv, f"sphere from {pos}")
+        assert hits > 1000
+        assert res[(True, True)] < 0.5 * so      # skipping must actually skip
+
+
+def test_raycast_after_integration(G):
+    """Integrate the synthetic scene from several poses, raycast from each (config-2 style, small)."""
+    from oracle import oracle
+    from tsdf_b200 import scenes
+    n = (80, 80, 80)
+    dv = G.DeviceVolume(n, (3000,) * 3)
+    ov = oracle.OracleVolume(n, (3000,) * 3)
+    for f in range(0, 16, 3):
+        cam = scenes.orbit_camera(f, 16)
+        k, kinv = quarter_intrinsics(cam, 0.5)
+        depth = scenes.render_depth(cam, 320, 240)
+        dv.integrate(depth, cam.inv_pose, k, kinv)
+        ov.integrate(depth, cam.inv_pose, k, kinv)
+        check_raycast(G, dv, ov, 320, 240, cam.pose, kinv, f"orbit frame {f}")
+
+
+def test_raycast_camera_inside_and_axis_aligned(G):
+    """Origin inside the AABB (near_t = 0, NaN-tolerant far_t chain, GPURaycaster.cu:202-233), rays with
+    exactly-zero direction components, offset volume, anisotropic voxels."""
+    from oracle import oracle
+    from tsdf_b200 import scenes
+    n = (64, 48, 40)
+    phys = (2000, 2400, 1600)
+    off = (250.0, -100.0, 40.0)
+    dv = G.DeviceVolume(n, phys, offset=off)
+    ov = oracle.OracleVolume(n, phys)
+    ov.offset[:] = off
+    sdf = sphere_sdf(n, phys, ov.trunc, (1000, 1200, 800), 500)
+    ov.dist[:] = sdf
+    dv.upload_dist(sdf)
+    cam = scenes.PinholeCamera(100.0, 100.0, 80.0, 60.0)     # principal point on a pixel: centre ray has dir (0,0,1)
+    cam.move_to(1250.0, 1100.0, 100.0)                        # inside the (offset) volume
+    check_raycast(G, dv, ov, 160, 120, cam.pose, cam.kinv, "inside, axis aligned")
+    cam.move_to(1250.0, 1100.0, -900.0)
+    check_raycast(G, dv, ov, 160, 120, cam.pose, cam.kinv, "outside, axis aligned")
+    cam.move_to(5000.0, 5000.0, -900.0)                       # every ray misses the volume
+    res, hits, so = check_raycast(G, dv, ov, 160, 120, cam.pose, cam.kinv, "all miss")
+    assert hits == 0 and so == 0
+
+
+def test_raycast_low_edge_extrapolation_and_negative_volume(G):
+    """Random (non-SDF) data with sign changes everywhere, including the first half-voxel layer where the
+    reference extrapolates (GPURaycaster.cu:87-99): skipping must never hide a hit."""
+    from oracle import oracle
+    from tsdf_b200 import scenes
+    rng = np.random.default_rng(11)
+    n = (40, 40, 40)
+    dv = G.DeviceVolume(n, (3000,) * 3)
+    ov = oracle.OracleVolume(n, (3000,) * 3)
+    data = np.full(40 ** 3, ov.trunc, np.float32)
+    grid = data.reshape(40, 40, 40)
+    grid[:, :, 1] = 100 * ov.trunc            # extrapolation in the x=0 half voxel goes negative
+    grid[20:, 5:30, 10:12] = -ov.trunc * rng.random((20, 25, 2)).astype(np.float32)
+    grid[3, 3, 3] = np.nan
+    grid[30, 30, 30] = 0.0
+    ov.dist[:] = data
+    dv.upload_dist(data)
+    for pos in ((-800, 1500, 1400), (1500, 1500, -900), (3900, 1700, 3900), (1500, -2000, 1500)):
+        cam = scenes.PinholeCamera()
+        cam.move_to(*pos)
+        cam.look_at(1500, 1500, 1500)
+        k, kinv = quarter_intrinsics(cam, 0.25)
+        check_raycast(G, dv, ov, 160, 120, cam.pose, kinv, f"synthetic data from {pos}")
+
+
+def test_raycast_sample_cap(G):
+    """Rays longer than 4402 samples end as misses at the cap (GPURaycaster.cu:369); a surface beyond the
+    cap is NOT found, one just before it is."""
+    from oracle import oracle
+    from tsdf_b200 import scenes
+    n = (512, 8, 8)
+    phys = (3000, 3000, 3000)
+    dv = G.DeviceVolume(n, phys)
+    ov = oracle.OracleVolume(n, phys)
+    step = np.float64(np.float32(np.float64(ov.trunc) * 0.05))
+    for x_wall in (4300 * step, 4500 * step):
+        data = np.full(512 * 64, ov.trunc, np.float32).reshape(8, 8, 512)
+        xc = (np.arange(512) + 0.5) * ov.voxel[0]
+        data[:, :, :] = np.clip(x_wall - xc, -ov.trunc, ov.trunc).astype(np.float32)
+        ov.dist[:] = data.reshape(-1)
+        dv.upload_dist(data.reshape(-1))
+        cam = scenes.PinholeCamera(100.0, 100.0, 16.0, 12.0)
+        cam.move_to(-1.0, 1500.0, 1500.0)
+        cam.look_at(3000.0, 1500.0, 1500.0)
+        res, hits, so = check_raycast(G, dv, ov, 32, 24, cam.pose, cam.kinv, f"cap wall@{x_wall:.0f}")
+        if x_wall > 4402 * step:
+            assert hits == 0
+        else:
+            assert hits > 0
+
+
+def test_normals_kernel(G):
+    import torch
+    from oracle import oracle
+    rng = np.random.default_rng(3)
+    V = rng.normal(0, 1000, (48 * 64, 3)).astype(np.float32)
+    V[rng.random(48 * 64) < 0.2] = np.nan
+    V[100] = V[101]          # zero-length difference -> 0/0
+    Vd = G.dev(V.reshape(-1))
+    Nd = torch.empty_like(Vd)
+    G.check(G.lib.tsdf_b200_normals(64, 48, G.ptr(Vd), G.ptr(Nd), None))
+    torch.cuda.synchronize()
+    assert_bits_equal(Nd.cpu().numpy(), oracle.normals(64, 48, V), "normals")
+
+
+def test_reciprocal_division_selftest(G):
+    import ctypes as C
+    for b in (3000 / 512, 3000 / 128, 3000 / 1024, 20.0, 3000 / 200, 2500 / 72, 1.0, 0.37):
+        bad = C.c_ulonglong(123)
+        G.check(G.lib.tsdf_b200_selftest_division(np.float32(b), C.byref(bad)))
+        assert bad.value == 0, f"fdiv_recip differs from IEEE division for {bad.value} numerators at b={b}"
+
+
+# ------------------------------------------------------------------------------ level-2 object
+def test_volume_object_end_to_end(G, tmp_path):
+    """The host-buffer API kinfu reaches through TSDFVolume: integrate x N, raycast, save, load."""
+    import json, os
+    from oracle import oracle
+    from tsdf_b200 import Volume, scenes
+    n = (64, 64, 64)
+    vol = Volume(n, (3000.0,) * 3)
+    ov = oracle.OracleVolume(n, (3000,) * 3)
+    assert vol.trunc == ov.trunc and vol.max_weight == 15.0
+    for f in (0, 2, 5):
+        cam = scenes.orbit_camera(f, 12)
+        depth = scenes.render_depth(cam)
+        vol.integrate(depth, cam.inv_pose, cam.k, cam.kinv)
+        nu = ov.integrate(depth, cam.inv_pose, cam.k, cam.kinv)
+        assert vol.stats()[0] == nu
+    d, w = vol.read()
+    assert_bits_equal(d, ov.dist, "dist"); assert_bits_equal(w, ov.weight, "weight")
+    V, N = vol.raycast(640, 480, cam.pose, cam.kinv)
+    Vo, No, ko, so = ov.raycast(640, 480, cam.pose, cam.kinv)
+    assert_bits_equal(V, Vo, "vertices"); assert_bits_equal(N, No, "normals")
+    assert 0 < vol.stats()[1] < so
+    vol.set_skipping(False)
+    V2, N2 = vol.raycast(640, 480, cam.pose, cam.kinv)
+    assert_bits_equal(V2, Vo, "vertices (no skipping)")
+    assert vol.stats()[1] == so
+    # save -> load round trip keeps every bit, and a loaded volume integrates through its stored field
+    path = str(tmp_path / "v.tsdf")
+    vol.save(path)
+    assert os.path.getsize(path) == 68 + 64 ** 3 * 35
+    vol2 = Volume.load(path)
+    d2, w2 = vol2.read()
+    assert_bits_equal(d2, d, "dist after load"); assert_bits_equal(w2, w, "weight after load")
+    cam = scenes.orbit_camera(7, 12)
+    depth = scenes.render_depth(cam)
+    vol2.integrate(depth, cam.inv_pose, cam.k, cam.kinv)
+    ov.integrate(depth, cam.inv_pose, cam.k, cam.kinv)
+    d2, w2 = vol2.read()
+    assert_bits_equal(d2, ov.dist, "dist after load+integrate")
+    V3, _ = vol2.raycast(640, 480, cam.pose, cam.kinv)
+    assert_bits_equal(V3, ov.raycast(640, 480, cam.pose, cam.kinv)[0], "vertices after load")
+    vol.close(); vol2.close()
+
+
+def test_volume_save_matches_reference_file_layout(G, tmp_path):
+    """A freshly constructed 100^3/2000mm volume with offset (50,50,50) saves the reference fixture's
+    bytes (TestData/t_100_2000_50.tsdf) in every section except the uninitialised colours."""
+    import hashlib, json, os
+    from tsdf_b200 import Volume
+    g = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "t_100_2000_50.json")))
+    vol = Volume(g["size"], g["physical"])
+    vol.set_offset(*g["offset"])
+    path = str(tmp_path / "t.tsdf")
+    vol.save(path)
+    raw = open(path, "rb").read()
+    n = 100 ** 3
+    assert len(raw) == g["file_bytes"]
+    assert raw[:68].hex() == g["header_hex"]
+    sha = lambda b: hashlib.sha256(b).hexdigest()
+    assert sha(raw[68:68 + 4 * n]) == g["dist_sha256"]
+    assert sha(raw[68 + 4 * n:68 + 8 * n]) == g["weight_sha256"]
+    assert sha(raw[68 + 11 * n:]) == g["deform_sha256"]
+    vol.close()
+
+
+def test_volume_offset_and_clear_semantics(G):
+    """offset() after construction is added on top of the stored grid (TSDFVolume.cu:343); clear()
+    re-bakes the current offset into the grid (:841), so it is then applied twice."""
+    from oracle import oracle
+    from tsdf_b200 import Volume, scenes
+    n = (40, 40, 40)
+    vol = Volume(n, (3000.0,) * 3)
+    ov = oracle.OracleVolume(n, (3000,) * 3, with_deformation=True)
+    cam = scenes.orbit_camera(1, 12)
+    depth = scenes.render_depth(cam)
+    for step in range(2):
+        vol.set_offset(120.0, -60.0, 33.0); ov.offset[:] = (120.0, -60.0, 33.0)
+        vol.integrate(depth, cam.inv_pose, cam.k, cam.kinv)
+        ov.integrate(depth, cam.inv_pose, cam.k, cam.kinv)
+        d, w = vol.read()
+        assert_bits_equal(d, ov.dist, f"dist step {step}"); assert_bits_equal(w, ov.weight, f"weight step {step}")
+        V, N = vol.raycast(320, 240, cam.pose, cam.kinv)
+        assert_bits_equal(V, ov.raycast(320, 240, cam.pose, cam.kinv)[0], f"vertices step {step}")
+        vol.clear(); ov.clear()
+    vol.close()

@@ -36,7 +36,7 @@ _lib.oracle_clear.argtypes = [_vp, _vp, _vp, _u32, _u32, _u32, _f, _f, C.c_float
 _lib.oracle_integrate.restype = C.c_uint64
 _lib.oracle_integrate.argtypes = [_vp, _vp, _vp, _u32, _u32, _u32, _f, _f, _f, C.c_float, _f, _f, _f, _u32, _u32, _vp, _u32, _u32]
 _lib.oracle_raycast.restype = C.c_uint64
-_lib.oracle_raycast.argtypes = [_vp, _u32, _u32, _u32, _f, _f, _f, C.c_float, _f, _f, _f, _u32, _u32, _vp, _vp]
+_lib.oracle_raycast.argtypes = [_vp, _u32, _u32, _u32, _f, _f, _f, C.c_float, _f, _f, _f, _u32, _u32, _vp, _vp, _u32, _u32]
 _lib.oracle_normals.restype = None
 _lib.oracle_normals.argtypes = [_u32, _u32, _vp, _vp]
 _lib.oracle_hit_voxels.restype = None
@@ -98,7 +98,7 @@ class OracleVolume:
                                          self.trunc, _fp(_cm(inv_pose)), _fp(_cm(k)), _fp(_cm(kinv)), w, h,
                                          depth.ctypes.data, z_begin, z_end))
 
-    def raycast(self, w, h, pose, kinv, want_khit=True):
+    def raycast(self, w, h, pose, kinv, want_khit=True, y_begin=0, y_step=1, want_normals=True):
         pose = np.asarray(pose, np.float32)
         vertices = np.empty((h * w, 3), np.float32)
         khit = np.empty(h * w, np.int32) if want_khit else None
@@ -107,9 +107,11 @@ class OracleVolume:
         origin = _fv(pose[:3, 3])
         n = _lib.oracle_raycast(self.dist.ctypes.data, *self.size, _fp(self.voxel), _fp(smin), _fp(smax), self.trunc,
                                 _fp(origin), _fp(_cm(pose[:3, :3])), _fp(_cm(kinv)), w, h, vertices.ctypes.data,
-                                khit.ctypes.data if want_khit else None)
-        normals = np.empty((h * w, 3), np.float32)
-        _lib.oracle_normals(w, h, vertices.ctypes.data, normals.ctypes.data)
+                                khit.ctypes.data if want_khit else None, y_begin, y_step)
+        normals = None
+        if want_normals:
+            normals = np.empty((h * w, 3), np.float32)
+            _lib.oracle_normals(w, h, vertices.ctypes.data, normals.ctypes.data)
         return vertices, normals, khit, int(n)
 
 

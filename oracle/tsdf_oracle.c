@@ -259,17 +259,19 @@ static int near_far(f3 o, f3 d, f3 smin, f3 smax, float *near_t, float *far_t) {
 
 /* process_ray, GPURaycaster.cu:265-377, for every pixel.  vertices: 3 floats per pixel,
  * index y*w+x.  khit (optional): index k of the sample at which the ray terminated with
- * a hit, -1 for rays that end without one.  Returns the number of trilinear samples.  */
+ * a hit, -1 for rays that end without one.  Only image rows y_begin, y_begin+y_step, ... are
+ * processed (0,1 = all; used to time a bounded sample).  Returns the number of trilinear samples. */
 uint64_t oracle_raycast(const float *dist, uint32_t nx, uint32_t ny, uint32_t nz, const float voxel[3],
                         const float space_min_[3], const float space_max_[3], float trunc,
                         const float origin_[3], const float rot[9], const float kinv[9],
-                        uint32_t width, uint32_t height, float *vertices, int32_t *khit) {
+                        uint32_t width, uint32_t height, float *vertices, int32_t *khit,
+                        uint32_t y_begin, uint32_t y_step) {
     uint64_t n_samples = 0;
     f3 origin = { origin_[0], origin_[1], origin_[2] };
     f3 smin = { space_min_[0], space_min_[1], space_min_[2] };
     f3 smax = { space_max_[0], space_max_[1], space_max_[2] };
 #pragma omp parallel for schedule(dynamic, 4) reduction(+ : n_samples)
-    for (int64_t imy = 0; imy < (int64_t)height; imy++)
+    for (int64_t imy = y_begin; imy < (int64_t)height; imy += (y_step ? y_step : 1))
         for (uint32_t imx = 0; imx < width; imx++) {
             size_t idx = (size_t)imy * width + imx;
             uint16_t pix_x = (uint16_t)imx, pix_y = (uint16_t)imy;

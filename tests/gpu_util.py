@@ -48,7 +48,7 @@ class DeviceVolume:
         self.counter[0] = 0
         check(lib.tsdf_b200_integrate(ptr(self.dist), ptr(self.weight), ptr(self.deform), *self.n, fptr(self.voxel),
                                       fptr(self.offset_at_clear), fptr(self.offset), self.trunc, fptr(colmajor(inv_pose)),
-                                      fptr(colmajor(k)), fptr(colmajor(kinv)), w, h, ptr(d), z_begin, z_end, ptr(self.occ),
+                                      fptr(colmajor(k)), fptr(colmajor(kinv)), w, h, ptr(d), z_begin, z_end, 0, ptr(self.occ),
                                       C.c_void_p(self.counter.data_ptr()) if count else None, None), "integrate")
         torch.cuda.synchronize()
         return int(self.counter[0].item())

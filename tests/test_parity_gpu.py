@@ -296,24 +296,24 @@ def test_raycast_sample_cap(G):
     from oracle import oracle
     from tsdf_b200 import scenes
     n = (512, 8, 8)
-    phys = (3000, 3000, 3000)
+    phys = (3000, 46.875, 46.875)          # cubic 5.859375 mm voxels, a 3000 mm long bar
     dv = G.DeviceVolume(n, phys)
     ov = oracle.OracleVolume(n, phys)
     step = np.float64(np.float32(np.float64(ov.trunc) * 0.05))
+    assert 4500 * step < 3000
     for x_wall in (4300 * step, 4500 * step):
-        data = np.full(512 * 64, ov.trunc, np.float32).reshape(8, 8, 512)
         xc = (np.arange(512) + 0.5) * ov.voxel[0]
-        data[:, :, :] = np.clip(x_wall - xc, -ov.trunc, ov.trunc).astype(np.float32)
+        data = np.broadcast_to(np.clip(x_wall - xc, -ov.trunc, ov.trunc).astype(np.float32), (8, 8, 512)).copy()
         ov.dist[:] = data.reshape(-1)
         dv.upload_dist(data.reshape(-1))
-        cam = scenes.PinholeCamera(100.0, 100.0, 16.0, 12.0)
-        cam.move_to(-1.0, 1500.0, 1500.0)
-        cam.look_at(3000.0, 1500.0, 1500.0)
+        cam = scenes.PinholeCamera(20000.0, 20000.0, 16.0, 12.0)    # near-parallel rays down the bar
+        cam.move_to(-1.0, 23.4375, 23.4375)
+        cam.look_at(3000.0, 23.4375, 23.4375)
         res, hits, so = check_raycast(G, dv, ov, 32, 24, cam.pose, cam.kinv, f"cap wall@{x_wall:.0f}")
         if x_wall > 4402 * step:
             assert hits == 0
         else:
-            assert hits > 0
+            assert hits == 32 * 24
 
 
 def test_normals_kernel(G):

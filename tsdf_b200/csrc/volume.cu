@@ -202,7 +202,7 @@ extern "C" int tsdf_b200_volume_integrate(tsdf_b200_volume *v, const uint16_t *h
     if (v->counting) TSDF_CUDA_TRY(cudaMemsetAsync(v->d_counters, 0, sizeof(unsigned long long), v->stream));
     const float *deform = v->deform_identity ? nullptr : v->d_deform;
     int rc = tsdf_b200_integrate(v->d_dist, v->d_weight, deform, v->nx, v->ny, v->nz, v->vs, v->off_clear, v->off, v->trunc,
-                                 inv_pose, k, kinv, width, height, v->d_depth, 0, v->nz, v->d_occ,
+                                 inv_pose, k, kinv, width, height, v->d_depth, 0, v->nz, 0, v->d_occ,
                                  v->counting ? v->d_counters : nullptr, v->stream);
     if (rc) return rc;
     if (v->counting)

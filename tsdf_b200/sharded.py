@@ -1,0 +1,192 @@
+"""Device-resident engine over the level-1 C-ABI: one process per GPU, the volume sharded along Z.
+
+world == 1: the whole volume lives on this GPU; integrate and raycast are single kernel launches.
+world  > 1: rank r owns the Z-slab [z0, z1) (multiples of the 8-voxel brick) plus one redundant halo
+plane z1, fused by the same integrate kernel (every voxel depends only on itself and the frame, so the
+halo is bit-identical to its owner's copy without communication).  Raycast: every rank marches all
+rays through the samples whose interpolation cell starts in its slab and emits, per pixel, the key
+(k_hit << 32 | float_bits(sample)); ONE all-reduce(min) over NVLink picks the first hit along each ray
+(t_k is ray-independent, so the winning (k, sample) reproduces the single-GPU vertex bit for bit);
+every rank then resolves keys to vertices and normals.
+
+PyTorch provides device memory, the stream and torch.distributed — nothing else.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from .capi import lib, check, fptr, fvec, colmajor, volume_params
+
+BRICK = 8
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else None
+
+
+class ShardedEngine:
+    def __init__(self, n, physical, rank=0, world=1, stream=None, skipping=True):
+        self.n = tuple(int(x) for x in n)
+        self.physical = fvec(physical)
+        self.rank, self.world = rank, world
+        self.voxel, self.trunc = volume_params(self.n, self.physical)
+        self.offset = np.zeros(3, np.float32)
+        self.offset_at_clear = np.zeros(3, np.float32)
+        self.stream = C.c_void_p(stream if stream is not None else torch.cuda.current_stream().cuda_stream)
+        self.skipping = skipping
+        nz = self.n[2]
+        if world == 1:
+            self.z0, self.z1 = 0, nz
+        else:
+            bricks = (nz + BRICK - 1) // BRICK
+            per = (bricks + world - 1) // world
+            self.z0 = min(rank * per * BRICK, nz)
+            self.z1 = min((rank + 1) * per * BRICK, nz)
+        self.zs1 = min(self.z1 + 1, nz) if world > 1 else nz        # stored planes [z0, zs1)
+        planes = max(self.zs1 - self.z0, 1)
+        nvl = self.n[0] * self.n[1] * planes
+        self.local_n = (self.n[0], self.n[1], planes)
+        self.dist = torch.empty(nvl, dtype=torch.float32, device="cuda")
+        self.weight = torch.empty(nvl, dtype=torch.float32, device="cuda")
+        self.occ = torch.empty(lib.tsdf_b200_occupancy_bytes(*self.local_n), dtype=torch.uint8, device="cuda")
+        self.table = torch.empty(4416, dtype=torch.float32, device="cuda")
+        self.counters = torch.zeros(2, dtype=torch.int64, device="cuda")
+        self._pix = 0
+        check(lib.tsdf_b200_ray_table(self.trunc, _ptr(self.table), self.stream), "ray_table")
+        self.fastdiv = 1
+        for b in sorted(set(float(x) for x in self.voxel)):
+            bad = C.c_ulonglong(1)
+            check(lib.tsdf_b200_selftest_division(np.float32(b), C.byref(bad)), "selftest_division")
+            if bad.value:
+                self.fastdiv = 0
+        self.clear()
+        # kernels per step: integrate + raycast + normals (+ resolve when sharded; the all-reduce is NCCL's)
+        self.launches_per_step = 3 if world == 1 else 5
+
+    # ------------------------------------------------------------------------------------------
+    def clear(self):
+        check(lib.tsdf_b200_clear(_ptr(self.dist), _ptr(self.weight), *self.local_n, self.trunc, _ptr(self.occ),
+                                  self.stream), "clear")
+        self.offset_at_clear = self.offset.copy()
+
+    def _buffers(self, w, h):
+        if self._pix != w * h:
+            self._pix = w * h
+            self.vertices = torch.empty(w * h * 3, dtype=torch.float32, device="cuda")
+            self.normals = torch.empty(w * h * 3, dtype=torch.float32, device="cuda")
+            self.keys = torch.empty(w * h, dtype=torch.int64, device="cuda") if self.world > 1 else None
+
+    @staticmethod
+    def _mats(cam):
+        """Column-major float* views of the camera matrices, cached on the camera object."""
+        m = getattr(cam, "_cabi", None)
+        if m is None:
+            pose = np.asarray(cam.pose, np.float32)
+            arrs = [colmajor(cam.inv_pose), colmajor(cam.k), colmajor(cam.kinv), fvec(pose[:3, 3]), colmajor(pose[:3, :3])]
+            m = tuple(fptr(a) for a in arrs) + (arrs,)      # keep the arrays alive
+            cam._cabi = m
+        return m
+
+    def integrate(self, d_depth, cam, count=False):
+        """d_depth: (H, W) uint16 CUDA tensor.  Returns voxels rewritten (owned planes only) when count."""
+        h, w = d_depth.shape
+        if count:
+            self.counters[0] = 0
+        mats = self._mats(cam)[:3]
+        own, stored = self.z1 - self.z0, self.zs1 - self.z0
+        if own > 0:
+            check(lib.tsdf_b200_integrate(_ptr(self.dist), _ptr(self.weight), None, *self.local_n, fptr(self.voxel),
+                                          fptr(self.offset_at_clear), fptr(self.offset), self.trunc, *mats,
+                                          w, h, _ptr(d_depth), 0, own, self.z0, _ptr(self.occ),
+                                          C.c_void_p(self.counters.data_ptr()) if count else None, self.stream),
+                  "integrate")
+        if stored > own:      # redundant halo plane, not counted
+            check(lib.tsdf_b200_integrate(_ptr(self.dist), _ptr(self.weight), None, *self.local_n, fptr(self.voxel),
+                                          fptr(self.offset_at_clear), fptr(self.offset), self.trunc, *mats,
+                                          w, h, _ptr(d_depth), own, stored, self.z0, _ptr(self.occ), None, self.stream),
+                  "integrate halo")
+        if count:
+            return int(self.counters[0].item())
+        return None
+
+    def raycast(self, w, h, cam, count=False):
+        self._buffers(w, h)
+        _, _, kinv_p, origin_p, rot_p, _ = self._mats(cam)
+        smin = self.offset.copy()
+        smax = (self.offset + self.physical).astype(np.float32)
+        cnt = C.c_void_p(self.counters.data_ptr() + 8) if count else None
+        if count:
+            self.counters[1] = 0
+        occ = _ptr(self.occ) if self.skipping else None
+        if self.world == 1:
+            check(lib.tsdf_b200_raycast_ex(_ptr(self.dist), *self.n, fptr(self.voxel), fptr(smin), fptr(smax), self.trunc,
+                                           origin_p, rot_p, kinv_p,
+                                           w, h, _ptr(self.table), occ, _ptr(self.vertices), None, cnt, self.fastdiv,
+                                           self.stream), "raycast")
+        else:
+            import torch.distributed as dist
+            check(lib.tsdf_b200_raycast_slab(_ptr(self.dist), *self.n, self.z0, self.z0, self.z1, fptr(self.voxel),
+                                             fptr(smin), fptr(smax), self.trunc, origin_p, rot_p, kinv_p, w, h,
+                                             _ptr(self.table), occ, _ptr(self.keys), cnt, self.fastdiv, self.stream),
+                  "raycast_slab")
+            dist.all_reduce(self.keys, op=dist.ReduceOp.MIN)
+            check(lib.tsdf_b200_raycast_resolve(_ptr(self.keys), fptr(smin), fptr(smax), self.trunc, origin_p, rot_p,
+                                                kinv_p, w, h, _ptr(self.table), _ptr(self.vertices), None, self.stream), "resolve")
+        check(lib.tsdf_b200_normals(w, h, _ptr(self.vertices), _ptr(self.normals), self.stream), "normals")
+        if count:
+            return int(self.counters[1].item())
+        return None
+
+    def last_ray_stats(self):
+        """Hit pixels / NaN pixels of the last raycast (diagnostics for the bench line)."""
+        if self._pix == 0:
+            return None
+        v = self.vertices.view(-1, 3)[:, 0]
+        hits = int((~torch.isnan(v)).sum().item())
+        return {"hit_pixels": hits, "pixels": self._pix}
+
+    def e2e(self, frames, cams, warmup, steps, w, h):
+        """Host-buffer loop for the sharded case: pinned depth H2D on every rank, result D2H on rank 0."""
+        import time
+        import torch.distributed as dist
+        pin = [torch.from_numpy(f).pin_memory() for f in frames]
+        d = torch.empty((h, w), dtype=torch.uint16, device="cuda")
+        hv = torch.empty(w * h * 3, dtype=torch.float32).pin_memory()
+        hn = torch.empty(w * h * 3, dtype=torch.float32).pin_memory()
+
+        def one(i):
+            d.copy_(pin[i], non_blocking=True)
+            self.integrate(d, cams[i])
+            self.raycast(w, h, cams[i])
+            if self.rank == 0:
+                hv.copy_(self.vertices, non_blocking=True)
+                hn.copy_(self.normals, non_blocking=True)
+            torch.cuda.synchronize()
+
+        for i in range(warmup):
+            one(i)
+        dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for s in range(steps):
+            one(warmup + s)
+        dist.barrier()
+        torch.cuda.synchronize()
+        ms = (time.perf_counter() - t0) * 1e3 / steps
+        t = torch.tensor([ms], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+        return {"value": 1e3 / ms, "unit": "frames/s", "h2d_bytes_per_step": w * h * 2 * self.world,
+                "d2h_bytes_per_step": 2 * w * h * 3 * 4, "ms_per_step": ms,
+                "api": "ShardedEngine: pinned depth H2D on every rank, integrate+raycast, vertex+normal D2H on rank 0"}
+
+    def read_local(self):
+        torch.cuda.synchronize()
+        return self.dist.cpu().numpy(), self.weight.cpu().numpy()
+
+    def close(self):
+        for name in ("dist", "weight", "occ", "vertices", "normals", "keys"):
+            if hasattr(self, name):
+                setattr(self, name, None)
+        torch.cuda.empty_cache()

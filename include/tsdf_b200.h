@@ -79,6 +79,10 @@ int tsdf_b200_integrate(float *d_dist, float *d_weight, const float *d_deform,
                         uint32_t z_begin, uint32_t z_end, uint32_t z_base, uint8_t *d_occ,
                         unsigned long long *d_n_updated, void *stream);
 
+/* Test hook: tsdf_b200_integrate picks a specialised kernel when the camera is rigid with a
+ * conventional K (same result bits, fewer instructions); on != 0 forces the general kernel.  */
+void tsdf_b200_debug_force_generic_integrate(int on);
+
 /* Size in bytes of the occupancy grid for a volume (one byte per 8^3 brick). */
 size_t tsdf_b200_occupancy_bytes(uint32_t nx, uint32_t ny, uint32_t nz);
 

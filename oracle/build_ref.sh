@@ -1,0 +1,51 @@
+#!/bin/bash
+# Builds the REFERENCE's own CUDA implementation of the hot path for sm_100 into oracle/_ref/ (git-ignored):
+#   oracle/_ref/libref_cuda_O3.so  -O3 -fmad=false : the numerical oracle on the GPU box (never contracts FMAs,
+#                                                     like the reference's own -G build) and the "fair" speed row
+#   oracle/_ref/libref_cuda_G.so   -G               : the reference as shipped (kinfu.make:64)
+# Sources are compiled where they lie under /root/reference/src; nothing is copied into the repo.  Three
+# accommodations: Eigen is replaced by tsdf_b200/compat (Eigen is not vendored by the reference
+# and absent here), missing transitive includes are supplied with --pre-include, and TSDFVolume.cu's load
+# constructor needs `(bool)` on seven `success = ifs.read(...)` lines — applied by sed to a scratch copy under
+# oracle/_ref/build/ that is deleted after the build.  libpng is absent: the PNG function and the DepthImage
+# constructor the linked files reference are stubbed in oracle/ref_harness.cu (never called on this path).
+# TEST INFRASTRUCTURE ONLY.
+set -e
+HERE="$(cd "$(dirname "$0")" && pwd)"
+REF=${REF_SRC:-/root/reference/src}
+OUT="$HERE/_ref"
+[ -d "$REF" ] || { echo "reference sources not found at $REF; keeping prebuilt oracle/_ref"; exit 0; }
+if [ -f "$OUT/libref_cuda_O3.so" ] && [ -f "$OUT/libref_cuda_G.so" ] && \
+   [ "$OUT/libref_cuda_O3.so" -nt "$HERE/ref_harness.cu" ] && [ "$OUT/libref_cuda_O3.so" -nt "$HERE/build_ref.sh" ] && \
+   [ "$OUT/libref_cuda_O3.so" -nt "$HERE/../tsdf_b200/compat/eigen_compat.hpp" ]; then
+    exit 0
+fi
+mkdir -p "$OUT/build"
+NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
+PRE="--pre-include cstdint --pre-include cstdio --pre-include cstring --pre-include cassert --pre-include stdexcept --pre-include cmath --pre-include limits"
+INC="-I$HERE/../tsdf_b200/compat -I$REF/include -I$REF"
+sed 's/success = ifs\.read/success = (bool)ifs.read/' "$REF/TSDF/TSDFVolume.cu" | \
+    sed 's#"\.\./include/#"'"$REF"'/include/#' > "$OUT/build/TSDFVolume_patched.cu"
+SRCS="$OUT/build/TSDFVolume_patched.cu $REF/TSDF/TSDF_utilities.cu $REF/Utilities/cuda_coordinate_transforms.cu \
+      $REF/Utilities/cuda_utilities.cu $REF/RayCaster/GPURaycaster.cu $HERE/ref_harness.cu"
+HOST="$REF/Camera.cpp $REF/Utilities/Definitions.cpp"
+build() {   # $1 = tag, rest = flags
+    tag=$1; shift
+    objs=""
+    for f in $SRCS; do
+        o="$OUT/build/$(basename "${f%.*}")_$tag.o"
+        $NVCC -gencode arch=compute_100a,code=sm_100a "$@" -std=c++11 -w -dc -Xcompiler -fPIC $PRE $INC -c "$f" -o "$o" &
+        objs="$objs $o"
+    done
+    for f in $HOST; do
+        o="$OUT/build/$(basename "${f%.*}")_$tag.o"
+        $NVCC -std=c++11 -O2 -w -Xcompiler -fPIC $PRE $INC -x cu -c "$f" -o "$o" &
+        objs="$objs $o"
+    done
+    wait
+    $NVCC -gencode arch=compute_100a,code=sm_100a -shared -o "$OUT/libref_cuda_$tag.so" $objs
+}
+build O3 -O3 -fmad=false -lineinfo
+build G -G
+rm -rf "$OUT/build"
+echo "built $OUT/libref_cuda_O3.so and $OUT/libref_cuda_G.so"

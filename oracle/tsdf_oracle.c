@@ -330,6 +330,103 @@ uint64_t oracle_raycast(const float *dist, uint32_t nx, uint32_t ny, uint32_t nz
     return n_samples;
 }
 
+/* ---- Z-sharded raycast (no reference counterpart: the reference is single-GPU) ----------------------------
+ * Statement of the decomposition the multi-GPU path uses, so that it can be checked on the CPU: a rank that
+ * owns the cells starting in [z_lo, z_hi) walks process_ray's loop but evaluates only its own samples (the
+ * others count as "no hit here"); key = (k << 32 | bits(sample)) of its first hit, INT64_MAX if none.  The
+ * minimum key over ranks is the first hit of the undivided loop, and oracle_resolve turns it into the vertex
+ * with process_ray's formula (GPURaycaster.cu:336-348).                                                     */
+static int cell_start_z(f3 p, uint32_t nz, const float vs[3]) {
+    float mz = nz * vs[2];
+    float adj = p.z;
+    if (p.z >= mz) adj = mz - (vs[2] / 10.0f);
+    if (p.z < 0.0f) adj = 0.0f;
+    int vz = gpu_f2i(floorf(adj / vs[2]));
+    float ctr = (vz + 0.5f) * vs[2] + 0.0f;
+    int lz = (p.z < ctr) ? vz - 1 : vz;
+    if (lz < 0) lz = 0;
+    return lz;
+}
+
+static void ray_setup(const float origin_[3], const float rot[9], const float kinv[9], const float smin_[3],
+                      const float smax_[3], uint32_t imx, uint32_t imy, f3 *dir, f3 *start, float *max_t, int *intersects) {
+    f3 origin = { origin_[0], origin_[1], origin_[2] };
+    f3 smin = { smin_[0], smin_[1], smin_[2] }, smax = { smax_[0], smax_[1], smax_[2] };
+    uint16_t pix_x = (uint16_t)imx, pix_y = (uint16_t)imy;
+    f3 rc = { pix_x * M3(kinv,1,1) + pix_y * M3(kinv,1,2) + M3(kinv,1,3),
+              pix_x * M3(kinv,2,1) + pix_y * M3(kinv,2,2) + M3(kinv,2,3),
+              pix_x * M3(kinv,3,1) + pix_y * M3(kinv,3,2) + M3(kinv,3,3) };
+    dir->x = M3(rot,1,1) * rc.x + M3(rot,1,2) * rc.y + M3(rot,1,3) * rc.z;
+    dir->y = M3(rot,2,1) * rc.x + M3(rot,2,2) * rc.y + M3(rot,2,3) * rc.z;
+    dir->z = M3(rot,3,1) * rc.x + M3(rot,3,2) * rc.y + M3(rot,3,3) * rc.z;
+    float near_t, far_t;
+    *intersects = near_far(origin, *dir, smin, smax, &near_t, &far_t);
+    start->x = (dir->x * near_t + origin.x) - smin.x;
+    start->y = (dir->y * near_t + origin.y) - smin.y;
+    start->z = (dir->z * near_t + origin.z) - smin.z;
+    *max_t = far_t - near_t;
+}
+
+void oracle_raycast_slab(const float *dist, uint32_t nx, uint32_t ny, uint32_t nz, uint32_t z_lo, uint32_t z_hi,
+                         const float voxel[3], const float space_min[3], const float space_max[3], float trunc,
+                         const float origin[3], const float rot[9], const float kinv[9],
+                         uint32_t width, uint32_t height, int64_t *keys) {
+#pragma omp parallel for schedule(dynamic, 4)
+    for (int64_t imy = 0; imy < (int64_t)height; imy++)
+        for (uint32_t imx = 0; imx < width; imx++) {
+            f3 dir, start; float max_t; int intersects;
+            ray_setup(origin, rot, kinv, space_min, space_max, imx, (uint32_t)imy, &dir, &start, &max_t, &intersects);
+            int64_t key = INT64_MAX;
+            if (intersects) {
+                float t = 0, step_size = (float)((double)trunc * 0.05);
+                int count = 0, done = 0;
+                while (!done) {
+                    f3 cp = { dir.x * t + start.x, dir.y * t + start.y, dir.z * t + start.z };
+                    int lz = cell_start_z(cp, nz, voxel);
+                    float tsdf = trunc;                                   /* not mine: behaves like a positive sample */
+                    if ((uint32_t)lz >= z_lo && (uint32_t)lz < z_hi) tsdf = trilinear(cp, nx, ny, nz, voxel, dist);
+                    if (tsdf <= 0) {
+                        uint32_t bits; memcpy(&bits, &tsdf, 4);
+                        key = ((int64_t)count << 32) | (int64_t)bits;
+                        done = 1;
+                    } else {
+                        t = t + step_size;
+                        if (t >= max_t) done = 1;
+                    }
+                    if (count++ > 4400) done = 1;
+                }
+            }
+            keys[(size_t)imy * width + imx] = key;
+        }
+}
+
+void oracle_resolve(const int64_t *keys, const float space_min[3], const float space_max[3], float trunc,
+                    const float origin[3], const float rot[9], const float kinv[9],
+                    uint32_t width, uint32_t height, float *vertices, int32_t *khit) {
+    float step_size = (float)((double)trunc * 0.05);
+    for (uint32_t imy = 0; imy < height; imy++)
+        for (uint32_t imx = 0; imx < width; imx++) {
+            size_t idx = (size_t)imy * width + imx;
+            f3 ip = { NAN, NAN, NAN };
+            int32_t kh = -1;
+            if (keys[idx] != INT64_MAX) {
+                kh = (int32_t)(keys[idx] >> 32);
+                uint32_t bits = (uint32_t)(keys[idx] & 0xffffffff);
+                float s; memcpy(&s, &bits, 4);
+                f3 dir, start; float max_t; int intersects;
+                ray_setup(origin, rot, kinv, space_min, space_max, imx, imy, &dir, &start, &max_t, &intersects);
+                float t = 0;
+                for (int k = 0; k < kh; k++) t = t + step_size;          /* t_k by repeated addition (:360) */
+                if (s < 0) { t = t - step_size; t = t + (trunc / (trunc - s)) * step_size; }
+                ip.x = (dir.x * t + start.x) + space_min[0];
+                ip.y = (dir.y * t + start.y) + space_min[1];
+                ip.z = (dir.z * t + start.z) + space_min[2];
+            }
+            vertices[3 * idx + 0] = ip.x; vertices[3 * idx + 1] = ip.y; vertices[3 * idx + 2] = ip.z;
+            if (khit) khit[idx] = kh;
+        }
+}
+
 /* compute_normals kernel, GPURaycaster.cu:393-427 */
 void oracle_normals(uint32_t width, uint32_t height, const float *V, float *N) {
 #pragma omp parallel for schedule(static)

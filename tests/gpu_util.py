@@ -76,3 +76,40 @@ class DeviceVolume:
         if self.occ is not None:
             check(lib.tsdf_b200_occupancy_rebuild(ptr(self.dist), *self.n, self.trunc, ptr(self.occ), None))
         torch.cuda.synchronize()
+
+
+def raycast_sharded_on_one_gpu(dv, w, h, pose, kinv, world, skip=True, fastdiv=True):
+    """Emulates the multi-GPU raycast on one device: the volume is cut into `world` Z-slabs (own planes + halo),
+    each slab is marched by tsdf_b200_raycast_slab from its own copy and its own occupancy grid, the keys are
+    min-reduced (what the NCCL all-reduce does) and resolved."""
+    from tsdf_b200.sharded import shard_ranges
+    pose = np.asarray(pose, np.float32)
+    nx, ny, nz = dv.n
+    smin = dv.offset.copy()
+    smax = (dv.offset + dv.physical).astype(np.float32)
+    keys = None
+    total = 0
+    full = dv.dist.view(nz, ny * nx)
+    for z0, z1 in shard_ranges(nz, world):
+        if z1 <= z0:
+            continue
+        zs1 = min(z1 + 1, nz)
+        slab = full[z0:zs1].contiguous().view(-1)
+        occ = torch.zeros(lib.tsdf_b200_occupancy_bytes(nx, ny, zs1 - z0), dtype=torch.uint8, device="cuda")
+        check(lib.tsdf_b200_occupancy_rebuild(ptr(slab), nx, ny, zs1 - z0, dv.trunc, ptr(occ), None))
+        k = torch.empty(h * w, dtype=torch.int64, device="cuda")
+        cnt = torch.zeros(1, dtype=torch.int64, device="cuda")
+        check(lib.tsdf_b200_raycast_slab(ptr(slab), nx, ny, nz, z0, zs1 - z0, z0, z1, fptr(dv.voxel), fptr(smin), fptr(smax),
+                                         dv.trunc, fptr(fvec(pose[:3, 3])), fptr(colmajor(pose[:3, :3])), fptr(colmajor(kinv)),
+                                         w, h, ptr(dv.table), ptr(occ) if skip else None, ptr(k), ptr(cnt), int(fastdiv), None),
+              "raycast_slab")
+        torch.cuda.synchronize()
+        total += int(cnt.item())
+        keys = k if keys is None else torch.minimum(keys, k)
+    V = torch.empty(h * w * 3, dtype=torch.float32, device="cuda")
+    kh = torch.empty(h * w, dtype=torch.int32, device="cuda")
+    check(lib.tsdf_b200_raycast_resolve(ptr(keys), fptr(smin), fptr(smax), dv.trunc, fptr(fvec(pose[:3, 3])),
+                                        fptr(colmajor(pose[:3, :3])), fptr(colmajor(kinv)), w, h, ptr(dv.table), ptr(V), ptr(kh), None),
+          "resolve")
+    torch.cuda.synchronize()
+    return V.cpu().numpy().reshape(-1, 3), kh.cpu().numpy(), total

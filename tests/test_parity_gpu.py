@@ -352,6 +352,66 @@ def test_raycast_sample_cap(G):
             assert hits == 32 * 24
 
 
+def test_raycast_random_volumes_stress(G):
+    """Randomised stress of the exact skipping logic: blobby random fields with many sign changes, thin shells,
+    isolated non-positive voxels and NaNs, random cameras (inside and outside), anisotropic voxels, offsets."""
+    from oracle import oracle
+    from tsdf_b200 import scenes
+    rng = np.random.default_rng(4242)
+    for trial in range(6):
+        n = tuple(int(x) for x in rng.integers(17, 72, size=3))
+        phys = tuple(float(x) for x in rng.uniform(1500, 3500, size=3))
+        off = tuple(float(x) for x in rng.uniform(-200, 200, size=3))
+        dv = G.DeviceVolume(n, phys, offset=off)
+        ov = oracle.OracleVolume(n, phys)
+        ov.offset[:] = off
+        z, y, x = np.meshgrid(*(np.linspace(0, 1, m) for m in (n[2], n[1], n[0])), indexing="ij")
+        f = np.zeros(x.shape)
+        for _ in range(4):
+            c = rng.uniform(0.1, 0.9, size=3); r = rng.uniform(0.1, 0.35)
+            f = np.maximum(f, r - np.sqrt((x - c[0]) ** 2 + (y - c[1]) ** 2 + (z - c[2]) ** 2))
+        data = np.where(f > 0, -f * 4000, ov.trunc).astype(np.float32)
+        data = np.clip(data, -ov.trunc, ov.trunc)
+        sel = rng.random(data.shape) < 0.0005
+        data[sel] = rng.choice(np.array([0.0, -1.0, np.nan, 1e-6, 1e9], np.float32), size=int(sel.sum()))
+        if trial % 2:
+            data[:, :, :2] = rng.uniform(-1, 1, size=data[:, :, :2].shape).astype(np.float32) * ov.trunc   # noisy low edge
+        ov.dist[:] = data.reshape(-1)
+        dv.upload_dist(data.reshape(-1))
+        centre = np.asarray(off) + 0.5 * np.asarray(phys)
+        for view in range(3):
+            cam = random_rigid_pose(rng, centre=centre, radius=(300.0, 800.0) if view == 2 else (2000.0, 5000.0))
+            k, kinv = quarter_intrinsics(cam, 0.25)
+            check_raycast(G, dv, ov, 160, 120, cam.pose, kinv, f"stress trial {trial} view {view}")
+
+
+def test_raycast_z_sharded_equals_whole(G):
+    """The multi-GPU decomposition on one device: slab copies with a halo plane, per-slab occupancy, key
+    min-reduction, resolve == the oracle's undivided march (vertices, hit index) for 1..5 shards."""
+    from oracle import oracle
+    from tsdf_b200 import scenes
+    n = (64, 56, 72)
+    dv = G.DeviceVolume(n, (3000,) * 3)
+    ov = oracle.OracleVolume(n, (3000,) * 3)
+    for f in (0, 5, 11):
+        cam = scenes.orbit_camera(f, 16)
+        k, kinv = quarter_intrinsics(cam, 0.5)
+        depth = scenes.render_depth(cam, 320, 240)
+        dv.integrate(depth, cam.inv_pose, k, kinv)
+        ov.integrate(depth, cam.inv_pose, k, kinv)
+    for f in (2, 6, 13):
+        cam = scenes.orbit_camera(f, 16)
+        k, kinv = quarter_intrinsics(cam, 0.5)
+        Vo, No, ko, so = ov.raycast(320, 240, cam.pose, kinv)
+        for world in (1, 2, 3, 5):
+            for skip in (False, True):
+                V, kh, ns = G.raycast_sharded_on_one_gpu(dv, 320, 240, cam.pose, kinv, world, skip=skip)
+                assert np.array_equal(kh, ko), f"frame {f} world {world} skip {skip}: hit index"
+                assert_bits_equal(V, Vo, f"frame {f} world {world} skip {skip}: vertices")
+                if not skip:
+                    assert ns <= so + 320 * 240 * 8 * world      # shards only re-evaluate the few samples at slab seams
+
+
 def test_normals_kernel(G):
     import torch
     from oracle import oracle

@@ -28,8 +28,12 @@ struct RayParams {
     uint32_t width, height;
     const float *table;
     const uint8_t *occ;
+    uint32_t nbx, nby, nbz;      // occupancy grid dimensions (local planes when sharded)
+    float occ_lo, occ_hi;        // positive band
+    uint32_t z_base, z_lo, z_hi; // Z-slab: global z of array plane 0; cells owned by this rank start in [z_lo, z_hi)
     float *vertices;
     int32_t *khit;
+    long long *keys;
     unsigned long long *n_samples;
 };
 
@@ -78,7 +82,53 @@ __device__ __forceinline__ bool near_far(const float o[3], const float d[3], con
            can_intersect(smin[2], smax[2], o[2], d[2], near_t, far_t);
 }
 
-template <bool FASTDIV, bool SKIP>
+// Per-ray set-up shared by the march and the resolve kernel: direction, clip, start point.
+struct RaySetup { float dir[3], start[3], max_t; bool intersects; };
+
+__device__ __forceinline__ RaySetup ray_setup(const RayParams &P, uint32_t imx, uint32_t imy) {
+    RaySetup r;
+    // compute_ray_direction_at_pixel (:24-44): uint16 pixel coords, K^-1 then R, NOT normalised.
+    const float fx = (float)(int)(uint16_t)imx, fy = (float)(int)(uint16_t)imy;
+    float rc[3];
+#pragma unroll
+    for (int i = 1; i <= 3; i++)
+        rc[i - 1] = fadd(fadd(fmul(fx, T33(P.kinv, i, 1)), fmul(fy, T33(P.kinv, i, 2))), T33(P.kinv, i, 3));
+#pragma unroll
+    for (int i = 1; i <= 3; i++)
+        r.dir[i - 1] = fadd(fadd(fmul(T33(P.rot, i, 1), rc[0]), fmul(T33(P.rot, i, 2), rc[1])), fmul(T33(P.rot, i, 3), rc[2]));
+    float near_t, far_t;
+    r.intersects = near_far(P.origin, r.dir, P.smin, P.smax, near_t, far_t);
+#pragma unroll
+    for (int a = 0; a < 3; a++) r.start[a] = fsub(fadd(fmul(r.dir[a], near_t), P.origin[a]), P.smin[a]);   // :306
+    r.max_t = fsub(far_t, near_t);                                                                         // :317
+    return r;
+}
+
+// Vertex of a hit at sample k with interpolated value s (:336-348); previous_tsdf == trunc always.
+__device__ __forceinline__ void hit_vertex(const RayParams &P, const RaySetup &r, float t, float s, float ip[3]) {
+    float th = t;
+    if (s < 0) {
+        th = fsub(th, P.step);                                                     // :338
+        th = fadd(th, fmul(fdiv(P.trunc, fsub(P.trunc, s)), P.step));              // :341
+    }
+#pragma unroll
+    for (int a = 0; a < 3; a++) ip[a] = fadd(fadd(fmul(r.dir[a], th), r.start[a]), P.smin[a]);  // :345-348
+}
+
+// Largest j >= 0 such that samples k+1 .. k+j all have t <= t_lim (0 if none), using the monotone table.
+__device__ __forceinline__ int safe_steps(const float *s_t, int k, float t, float t_gain, float inv_step) {
+    if (!(t_gain > 0.0f) || !(t_gain < 1.0e9f)) return 0;
+    int j = (int)(t_gain * inv_step * 0.999f);
+    if (j <= 0) return 0;
+    if (k + j > TSDF_B200_MAX_SAMPLES) j = TSDF_B200_MAX_SAMPLES - k;
+    const float t_lim = t + t_gain;
+    while (j > 0 && !(s_t[k + j] <= t_lim)) j--;
+    return j;
+}
+
+// One thread per pixel.  SLAB: the volume arrays hold planes [z_base, z_base + nz_local) of a Z-sharded volume,
+// only samples whose interpolation cell starts in [z_lo, z_hi) are evaluated, and the result is a key.
+template <bool FASTDIV, bool SKIP, bool SLAB>
 __global__ void __launch_bounds__(128)
 raycast_kernel(const __grid_constant__ RayParams P) {
     __shared__ float s_t[TSDF_B200_RAY_TABLE_LEN];
@@ -93,46 +143,66 @@ raycast_kernel(const __grid_constant__ RayParams P) {
 
     if (imx < P.width && imy < P.height) {
         const size_t pix = (size_t)imy * P.width + imx;
-        // compute_ray_direction_at_pixel (:24-44): uint16 pixel coords, K^-1 then R, NOT normalised.
-        const float fx = (float)(int)(uint16_t)imx, fy = (float)(int)(uint16_t)imy;
-        float rc[3], dir[3];
-#pragma unroll
-        for (int r = 1; r <= 3; r++)
-            rc[r - 1] = fadd(fadd(fmul(fx, T33(P.kinv, r, 1)), fmul(fy, T33(P.kinv, r, 2))), T33(P.kinv, r, 3));
-#pragma unroll
-        for (int r = 1; r <= 3; r++)
-            dir[r - 1] = fadd(fadd(fmul(T33(P.rot, r, 1), rc[0]), fmul(T33(P.rot, r, 2), rc[1])), fmul(T33(P.rot, r, 3), rc[2]));
-
-        float near_t, far_t;
-        const bool intersects = near_far(P.origin, dir, P.smin, P.smax, near_t, far_t);
+        const RaySetup R = ray_setup(P, imx, imy);
         float ip[3] = { CUDART_NAN_F, CUDART_NAN_F, CUDART_NAN_F };
         int kh = -1;
+        float s_hit = 0.0f;
 
-        if (intersects) {
-            float start[3];
-#pragma unroll
-            for (int a = 0; a < 3; a++) start[a] = fsub(fadd(fmul(dir[a], near_t), P.origin[a]), P.smin[a]);   // :306
-            const float max_t = fsub(far_t, near_t);                                                           // :317
+        if (R.intersects) {
+            const float *dir = R.dir, *start = R.start;
+            const float max_t = R.max_t;
             const float step = P.step;
             const float mx[3] = { fmul((float)P.nx, P.vs[0]), fmul((float)P.ny, P.vs[1]), fmul((float)P.nz, P.vs[2]) };
             const float hi_adj[3] = { fsub(mx[0], fdiv(P.vs[0], 10.0f)), fsub(mx[1], fdiv(P.vs[1], 10.0f)), fsub(mx[2], fdiv(P.vs[2], 10.0f)) };
-            const BrickDims nb = brick_dims(P.nx, P.ny, P.nz);
-            float inv_dir[3];
+            const float inv_step = __frcp_rn(step);
+            // Skipping helpers (approximate arithmetic, only ever used conservatively):
+            //   ainv = 1/|dir|, dt = parameter length of one brick, et = parameter length of the 2%-of-a-voxel guard band
+            float ainv[3], dtb[3], et[3];
+            int sgn[3];
             if (SKIP) {
 #pragma unroll
-                for (int a = 0; a < 3; a++) inv_dir[a] = __frcp_rn(dir[a]);    // approximate use only
+                for (int a = 0; a < 3; a++) {
+                    const float ad = fabsf(dir[a]);
+                    const bool moving = ad > 0.0f && ad < 3.0e38f;
+                    ainv[a] = moving ? __frcp_rn(ad) : 0.0f;
+                    sgn[a] = !moving ? 0 : (dir[a] > 0.0f ? 1 : -1);
+                    dtb[a] = moving ? (float)TSDF_B200_BRICK * P.vs[a] * ainv[a] : 3.0e30f;
+                    et[a] = moving ? 0.02f * P.vs[a] * ainv[a] : 0.0f;
+                }
             }
-            const float inv_step = __frcp_rn(step);
 
             int clx = -1, cly = -1, clz = -1;     // corner cache key
             float c000 = 0, c001 = 0, c010 = 0, c011 = 0, c100 = 0, c101 = 0, c110 = 0, c111 = 0;
+            bool cpos = false;                    // all 8 cached corners inside the positive band
 
-            int k = 0;
+            int k = 0, k_stop = TSDF_B200_MAX_SAMPLES - 1;     // samples k = 0..4401 exist (:369)
+            if (SLAB) {
+                // Parameter interval in which a sample's cell can start inside [z_lo, z_hi), with a voxel of slack.
+                const float zl = (P.z_lo == 0) ? -3.0e38f : ((float)P.z_lo - 1.0f) * P.vs[2];
+                const float zh = (P.z_hi >= P.nz) ? 3.0e38f : ((float)P.z_hi + 1.5f) * P.vs[2];
+                float ta = 0.0f, tb = 3.0e38f;
+                if (dir[2] > 0.0f)      { ta = (zl - start[2]) / dir[2]; tb = (zh - start[2]) / dir[2]; }
+                else if (dir[2] < 0.0f) { ta = (zh - start[2]) / dir[2]; tb = (zl - start[2]) / dir[2]; }
+                else if (start[2] < zl || start[2] > zh) { tb = -1.0f; }
+                if (tb < 0.0f) k = k_stop + 1;                       // never inside this slab
+                else {
+                    if (ta > 0.0f && ta < 1.0e9f) {
+                        int ka = (int)(ta * inv_step) - 3;
+                        if (ka > k_stop) ka = k_stop + 1;
+                        while (ka > 0 && ka <= k_stop && s_t[ka] > ta) ka--;
+                        if (ka > 0) k = ka;
+                    }
+                    if (tb < 1.0e9f) {
+                        int kb = (int)(tb * inv_step) + 4;
+                        if (kb < k_stop) k_stop = kb;
+                    }
+                }
+            }
+
             while (true) {
-                // Samples k = 0..4401 exist (:369); sample k>0 exists only if t_k < max_t (:360-365).
-                if (k > TSDF_B200_MAX_SAMPLES - 1) break;
+                if (k > k_stop) break;
                 const float t = s_t[k];
-                if (k > 0 && t >= max_t) break;
+                if (k > 0 && t >= max_t) break;                         // sample k>0 exists only if t_k < max_t (:360-365)
 
                 float p[3];
 #pragma unroll
@@ -150,34 +220,64 @@ raycast_kernel(const __grid_constant__ RayParams P) {
                 const bool oob = vox[0] < 0 || vox[1] < 0 || vox[2] < 0 ||
                                  (uint32_t)vox[0] >= P.nx || (uint32_t)vox[1] >= P.ny || (uint32_t)vox[2] >= P.nz;
 
-                if (SKIP && !oob) {
-                    const int bx = vox[0] / TSDF_B200_BRICK, by = vox[1] / TSDF_B200_BRICK, bz = vox[2] / TSDF_B200_BRICK;
-                    // Low-edge half voxel extrapolates (:87-99): never skip a sample in voxel layer 0.
-                    if (vox[0] >= 1 && vox[1] >= 1 && vox[2] >= 1 &&
-                        __ldg(P.occ + ((size_t)bz * nb.by + by) * nb.bx + bx) == 0) {
-                        // This sample is > 0 for sure.  How many of the following samples stay inside the
-                        // brick (conservatively)?  Exit distance along the ray, minus one step of margin.
-                        const int b[3] = { bx, by, bz };
-                        float t_exit = CUDART_INF_F;
+                // ---- level 1: runs of empty bricks ------------------------------------------------------
+                // A brick flag of 0 says every voxel of the brick and of its 1-voxel apron lies in the positive band,
+                // so any sample whose voxel is in the brick (and not in voxel layer 0, where the reference
+                // extrapolates, :87-99) is > 0.  From such a sample, walk the ray through consecutive empty bricks and
+                // jump to the last sample that is certainly still inside them.
+                if (SKIP && !oob && vox[0] >= 1 && vox[1] >= 1 && vox[2] >= 1) {
+                    int b[3] = { vox[0] / TSDF_B200_BRICK, vox[1] / TSDF_B200_BRICK, vox[2] / TSDF_B200_BRICK };
+                    const int bz_local = b[2] - (SLAB ? (int)(P.z_base / TSDF_B200_BRICK) : 0);
+                    const bool in_grid = !SLAB || (bz_local >= 0 && bz_local < (int)P.nbz);
+                    long bi = ((long)bz_local * P.nby + b[1]) * P.nbx + b[0];
+                    if (in_grid && __ldg(P.occ + bi) == 0) {
+                        // distances (in t) to the exit faces of the landing brick; the landing point must be clear of
+                        // every face by the guard band, otherwise just step once (this sample is known positive)
+                        float tm[3];
+                        bool clear = true;
 #pragma unroll
                         for (int a = 0; a < 3; a++) {
-                            // Brick faces pulled in by 1% of a voxel: >100x the rounding error of p
-                            // and of floor(p/voxel) for grids up to 65535 voxels per side.
-                            if (dir[a] > 0.0f) {
-                                float bound = ((float)((b[a] + 1) * TSDF_B200_BRICK) - 0.01f) * P.vs[a];
-                                t_exit = fminf(t_exit, (bound - p[a]) * inv_dir[a]);
-                            } else if (dir[a] < 0.0f) {
-                                float bound = ((b[a] == 0) ? 1.01f : (float)(b[a] * TSDF_B200_BRICK) + 0.01f) * P.vs[a];
-                                t_exit = fminf(t_exit, (bound - p[a]) * inv_dir[a]);
-                            }
+                            const float lo = ((b[a] == 0) ? 1.0f : (float)(b[a] * TSDF_B200_BRICK)) * P.vs[a];
+                            const float hi = (float)((b[a] + 1) * TSDF_B200_BRICK) * P.vs[a];
+                            const float dlo = p[a] - lo, dhi = hi - p[a];
+                            const float g = 0.02f * P.vs[a];
+                            clear = clear && dlo >= g && dhi >= g;
+                            tm[a] = sgn[a] > 0 ? dhi * ainv[a] : (sgn[a] < 0 ? dlo * ainv[a] : 1.0e30f);
                         }
                         int j = 0;
-                        if (t_exit > 2.0f * step && t_exit < 1.0e9f) {
-                            j = (int)(t_exit * inv_step * 0.999f) - 2;
-                            if (j < 0) j = 0;
-                            if (k + j > TSDF_B200_MAX_SAMPLES) j = TSDF_B200_MAX_SAMPLES - k;
-                            const float t_lim = t + t_exit - step;
-                            while (j > 0 && !(s_t[k + j] <= t_lim)) j--;
+                        if (clear) {
+                            const long stride[3] = { 1, (long)P.nbx, (long)P.nbx * P.nby };
+                            const int nb[3] = { (int)P.nbx, (int)P.nby, SLAB ? (int)P.nbz + (int)(P.z_base / TSDF_B200_BRICK) : (int)P.nbz };
+                            const int nb_lo_z = SLAB ? (int)(P.z_base / TSDF_B200_BRICK) : 0;
+                            for (int it = 0; it < 1024; it++) {
+                                const float tc = fminf(tm[0], fminf(tm[1], tm[2]));
+                                const int a = (tm[0] == tc) ? 0 : ((tm[1] == tc) ? 1 : 2);
+                                // the other two axes must be clear of their faces at the crossing (no corner grazing)
+                                bool ok = true;
+#pragma unroll
+                                for (int c = 0; c < 3; c++) {
+                                    const float rem = tm[c] - tc;
+                                    ok = ok && (c == a || (rem >= et[c] && rem <= dtb[c] - et[c]));
+                                }
+                                if (!ok) break;
+                                int nbk, lim_lo = 0, lim_hi, sg;
+                                long st;
+                                if (a == 0)      { nbk = b[0] + sgn[0]; lim_hi = nb[0]; sg = sgn[0]; st = stride[0]; }
+                                else if (a == 1) { nbk = b[1] + sgn[1]; lim_hi = nb[1]; sg = sgn[1]; st = stride[1]; }
+                                else             { nbk = b[2] + sgn[2]; lim_hi = nb[2]; sg = sgn[2]; st = stride[2]; lim_lo = nb_lo_z; }
+                                // never walk into brick layer 0 of an axis (the low-edge layer needs the voxel >= 1 test),
+                                // nor out of the grid / out of this rank's slab
+                                if (sg == 0 || nbk <= 0 || nbk < lim_lo || nbk >= lim_hi) break;
+                                const long nbi = bi + (sg > 0 ? st : -st);
+                                if (__ldg(P.occ + nbi) != 0) break;
+                                bi = nbi;
+                                if (a == 0)      { b[0] = nbk; tm[0] += dtb[0]; }
+                                else if (a == 1) { b[1] = nbk; tm[1] += dtb[1]; }
+                                else             { b[2] = nbk; tm[2] += dtb[2]; }
+                            }
+                            // exit of the last verified brick, pulled in by the guard band on every axis
+                            const float t_gain = fminf(tm[0] - et[0], fminf(tm[1] - et[1], tm[2] - et[2]));
+                            j = safe_steps(s_t, k, t, t_gain, inv_step);
                         }
                         k += 1 + j;
                         continue;
@@ -187,9 +287,10 @@ raycast_kernel(const __grid_constant__ RayParams P) {
                 float s;
                 if (oob) {
                     s = CUDART_NAN_F;                                                          // :77-80
+                    samples++;
                 } else {
                     int low[3];
-                    float uvw[3];
+                    float uvw[3], lcs[3];
 #pragma unroll
                     for (int a = 0; a < 3; a++) {
                         const float ctr = fadd(fmul(fadd((float)vox[a], 0.5f), P.vs[a]), 0.0f);      // TSDF_utilities.cu:10-17
@@ -198,13 +299,16 @@ raycast_kernel(const __grid_constant__ RayParams P) {
                         const float lc = fadd(fmul(fadd((float)l, 0.5f), P.vs[a]), 0.0f);
                         uvw[a] = div_vs<FASTDIV>(fsub(p[a], lc), P.vs[a], P.rvs[a]);             // :98-102
                         low[a] = l;
+                        lcs[a] = lc;
                     }
+                    if (SLAB && ((uint32_t)low[2] < P.z_lo || (uint32_t)low[2] >= P.z_hi)) { k++; continue; }   // another rank's sample
                     if (low[0] != clx || low[1] != cly || low[2] != clz) {
                         clx = low[0]; cly = low[1]; clz = low[2];
                         // tsdf_value_at (TSDF_utilities.cu:29-37): upper clamp, 32-bit index arithmetic
+                        const uint32_t zb = SLAB ? P.z_base : 0u;
                         const uint32_t x0 = min((uint32_t)clx, P.nx - 1), x1 = min((uint32_t)clx + 1, P.nx - 1);
                         const uint32_t y0 = P.nx * min((uint32_t)cly, P.ny - 1), y1 = P.nx * min((uint32_t)cly + 1, P.ny - 1);
-                        const uint32_t z0 = P.nx * P.ny * min((uint32_t)clz, P.nz - 1), z1 = P.nx * P.ny * min((uint32_t)clz + 1, P.nz - 1);
+                        const uint32_t z0 = P.nx * P.ny * (min((uint32_t)clz, P.nz - 1) - zb), z1 = P.nx * P.ny * (min((uint32_t)clz + 1, P.nz - 1) - zb);
                         c000 = __ldg(P.dist + (size_t)(z0 + y0 + x0));
                         c001 = __ldg(P.dist + (size_t)(z1 + y0 + x0));
                         c010 = __ldg(P.dist + (size_t)(z0 + y1 + x0));
@@ -213,8 +317,33 @@ raycast_kernel(const __grid_constant__ RayParams P) {
                         c101 = __ldg(P.dist + (size_t)(z1 + y0 + x1));
                         c110 = __ldg(P.dist + (size_t)(z0 + y1 + x1));
                         c111 = __ldg(P.dist + (size_t)(z1 + y1 + x1));
+                        if (SKIP) {
+                            const float cmin = fminf(fminf(fminf(c000, c001), fminf(c010, c011)), fminf(fminf(c100, c101), fminf(c110, c111)));
+                            const float cmax = fmaxf(fmaxf(fmaxf(c000, c001), fmaxf(c010, c011)), fmaxf(fmaxf(c100, c101), fmaxf(c110, c111)));
+                            const bool finite = (c000 == c000) && (c001 == c001) && (c010 == c010) && (c011 == c011) &&
+                                                (c100 == c100) && (c101 == c101) && (c110 == c110) && (c111 == c111);
+                            cpos = finite && cmin >= P.occ_lo && cmax <= P.occ_hi;
+                        }
                     }
                     const float u = uvw[0], v = uvw[1], w = uvw[2];
+
+                    // ---- level 2: a cell whose 8 corners are all in the positive band ----------------------------
+                    // With weights in [0,1] every product is >= 0 and one is >= corner/8 > 0, so the sample is > 0
+                    // without evaluating it; the same holds for every following sample that stays inside the cell
+                    // (pulled in by the guard band, so that `lower` and the weights' range cannot flip).
+                    if (SKIP && cpos && u >= 0.0f && u <= 1.0f && v >= 0.0f && v <= 1.0f && w >= 0.0f && w <= 1.0f) {
+                        float t_gain = 3.0e30f;
+#pragma unroll
+                        for (int a = 0; a < 3; a++) {
+                            const float g = 0.02f * P.vs[a];
+                            const float dlo = p[a] - (lcs[a] + g), dhi = (lcs[a] + P.vs[a] - g) - p[a];
+                            const float ta = sgn[a] > 0 ? dhi * ainv[a] : (sgn[a] < 0 ? dlo * ainv[a] : ((dlo >= 0.0f && dhi >= 0.0f) ? 3.0e30f : -1.0f));
+                            t_gain = fminf(t_gain, (dlo >= 0.0f && dhi >= 0.0f) ? ta : -1.0f);
+                        }
+                        k += 1 + safe_steps(s_t, k, t, t_gain, inv_step);
+                        continue;
+                    }
+
                     const float u1 = fsub(1.0f, u), v1 = fsub(1.0f, v), w1 = fsub(1.0f, w);
                     s = fmul(fmul(fmul(c000, u1), v1), w1);                                      // :114-121
                     s = fadd(s, fmul(fmul(fmul(c001, u1), v1), w));
@@ -224,33 +353,55 @@ raycast_kernel(const __grid_constant__ RayParams P) {
                     s = fadd(s, fmul(fmul(fmul(c101, u), v1), w));
                     s = fadd(s, fmul(fmul(fmul(c110, u), v), w1));
                     s = fadd(s, fmul(fmul(fmul(c111, u), v), w));
+                    samples++;
                 }
-                samples++;
 
                 if (s <= 0) {
-                    float th = t;
-                    if (s < 0) {
-                        th = fsub(th, step);                                                     // :338
-                        th = fadd(th, fmul(fdiv(P.trunc, fsub(P.trunc, s)), step));              // :341 (previous_tsdf == trunc)
-                    }
-#pragma unroll
-                    for (int a = 0; a < 3; a++) ip[a] = fadd(fadd(fmul(dir[a], th), start[a]), P.smin[a]);  // :345-348
                     kh = k;
+                    s_hit = s;
+                    if (!SLAB) hit_vertex(P, R, t, s, ip);
                     break;
                 }
                 k++;
             }
         }
-        P.vertices[3 * pix + 0] = ip[0];
-        P.vertices[3 * pix + 1] = ip[1];
-        P.vertices[3 * pix + 2] = ip[2];
-        if (P.khit) P.khit[pix] = kh;
+        if (SLAB) {
+            // key: first hit along the ray wins an all-reduce(min); the sample value rides in the low word
+            P.keys[pix] = (kh >= 0) ? (((long long)kh << 32) | (long long)(uint32_t)__float_as_uint(s_hit)) : 0x7fffffffffffffffLL;
+        } else {
+            P.vertices[3 * pix + 0] = ip[0];
+            P.vertices[3 * pix + 1] = ip[1];
+            P.vertices[3 * pix + 2] = ip[2];
+            if (P.khit) P.khit[pix] = kh;
+        }
     }
 
     if (P.n_samples) {
         for (int o = 16; o > 0; o >>= 1) samples += __shfl_down_sync(0xffffffffu, samples, o);
         if (lane == 0 && samples) atomicAdd(P.n_samples, (unsigned long long)samples);
     }
+}
+
+// Keys (after the min-reduction over ranks) -> vertices: the same per-ray set-up and hit formula as the march.
+__global__ void __launch_bounds__(128)
+resolve_kernel(const __grid_constant__ RayParams P) {
+    const uint32_t imx = blockIdx.x * 16 + (threadIdx.x & 15);
+    const uint32_t imy = blockIdx.y * 8 + (threadIdx.x >> 4);
+    if (imx >= P.width || imy >= P.height) return;
+    const size_t pix = (size_t)imy * P.width + imx;
+    const long long key = P.keys[pix];
+    float ip[3] = { CUDART_NAN_F, CUDART_NAN_F, CUDART_NAN_F };
+    int kh = -1;
+    if (key != 0x7fffffffffffffffLL) {
+        kh = (int)(key >> 32);
+        const float s = __uint_as_float((uint32_t)(key & 0xffffffffLL));
+        const RaySetup R = ray_setup(P, imx, imy);
+        hit_vertex(P, R, __ldg(P.table + kh), s, ip);
+    }
+    P.vertices[3 * pix + 0] = ip[0];
+    P.vertices[3 * pix + 1] = ip[1];
+    P.vertices[3 * pix + 2] = ip[2];
+    if (P.khit) P.khit[pix] = kh;
 }
 
 // compute_normals (GPURaycaster.cu:393-427)
@@ -327,44 +478,62 @@ extern "C" int tsdf_b200_selftest_division(float divisor, unsigned long long *mi
 static bool fastdiv_range_ok(float b) { return b > 1.0e-6f && b < 1.0e6f; }
 static bool sane(float x, float bound) { return x == x && fabsf(x) < bound; }
 
+static int fill_params(RayParams &P, const float *d_dist, uint32_t nx, uint32_t ny, uint32_t nz, const float voxel[3],
+                       const float space_min[3], const float space_max[3], float trunc, const float origin[3],
+                       const float rot[9], const float kinv[9], uint32_t width, uint32_t height, const float *d_table,
+                       int *fastdiv) {
+    if (!voxel || !space_min || !space_max || !origin || !rot || !kinv || !d_table) return TSDF_B200_EINVAL;
+    if (nx == 0 || ny == 0 || nz == 0 || width == 0 || height == 0) return TSDF_B200_EINVAL;
+    if (nx > 65535 || ny > 65535 || nz > 65535 || width > 65535 || height > 65535) return TSDF_B200_EINVAL;
+    if ((uint64_t)nx * ny * nz > 0xffffffffull) return TSDF_B200_EINVAL;   // reference indexes voxels in 32 bits
+    P.dist = d_dist; P.nx = nx; P.ny = ny; P.nz = nz;
+    for (int i = 0; i < 3; i++) {
+        P.vs[i] = voxel[i]; P.rvs[i] = 1.0f / voxel[i];
+        P.smin[i] = space_min[i]; P.smax[i] = space_max[i]; P.origin[i] = origin[i];
+        if (!fastdiv_range_ok(voxel[i]) || !sane(space_min[i], 1e12f) || !sane(space_max[i], 1e12f) || !sane(origin[i], 1e12f))
+            *fastdiv = 0;
+    }
+    for (int i = 0; i < 9; i++) if (!sane(rot[i], 1e6f) || !sane(kinv[i], 1e6f)) *fastdiv = 0;
+    P.trunc = trunc;
+    P.step = (float)((double)trunc * 0.05);
+    for (int i = 0; i < 9; i++) { P.rot.m[i] = rot[i]; P.kinv.m[i] = kinv[i]; }
+    P.width = width; P.height = height; P.table = d_table;
+    P.occ = nullptr; P.nbx = P.nby = P.nbz = 0;
+    P.occ_lo = trunc * kOccLoFrac; P.occ_hi = trunc * kOccHiFrac;
+    P.z_base = 0; P.z_lo = 0; P.z_hi = nz;
+    P.vertices = nullptr; P.khit = nullptr; P.keys = nullptr; P.n_samples = nullptr;
+    return 0;
+}
+
+template <bool SLAB>
+static int launch_march(const RayParams &P, int fastdiv, cudaStream_t s) {
+    dim3 block(128);
+    dim3 grid((P.width + 15) / 16, (P.height + 7) / 8);
+    if (fastdiv) {
+        if (P.occ) raycast_kernel<true, true, SLAB><<<grid, block, 0, s>>>(P);
+        else       raycast_kernel<true, false, SLAB><<<grid, block, 0, s>>>(P);
+    } else {
+        if (P.occ) raycast_kernel<false, true, SLAB><<<grid, block, 0, s>>>(P);
+        else       raycast_kernel<false, false, SLAB><<<grid, block, 0, s>>>(P);
+    }
+    return (int)cudaGetLastError();
+}
+
 extern "C" int tsdf_b200_raycast_ex(const float *d_dist, uint32_t nx, uint32_t ny, uint32_t nz,
                                     const float voxel[3], const float space_min[3], const float space_max[3],
                                     float trunc, const float origin[3], const float rot[9], const float kinv[9],
                                     uint32_t width, uint32_t height, const float *d_table,
                                     const uint8_t *d_occ, float *d_vertices, int32_t *d_khit,
                                     unsigned long long *d_n_samples, int fastdiv, void *stream) {
-    if (!d_dist || !voxel || !space_min || !space_max || !origin || !rot || !kinv || !d_table || !d_vertices)
-        return TSDF_B200_EINVAL;
-    if (nx == 0 || ny == 0 || nz == 0 || width == 0 || height == 0) return TSDF_B200_EINVAL;
-    if (nx > 65535 || ny > 65535 || nz > 65535 || width > 65535 || height > 65535) return TSDF_B200_EINVAL;
-    if ((uint64_t)nx * ny * nz > 0xffffffffull) return TSDF_B200_EINVAL;   // reference indexes voxels in 32 bits
-
+    if (!d_dist || !d_vertices) return TSDF_B200_EINVAL;
     RayParams P;
-    P.dist = d_dist; P.nx = nx; P.ny = ny; P.nz = nz;
-    for (int i = 0; i < 3; i++) {
-        P.vs[i] = voxel[i]; P.rvs[i] = 1.0f / voxel[i];
-        P.smin[i] = space_min[i]; P.smax[i] = space_max[i]; P.origin[i] = origin[i];
-        if (!fastdiv_range_ok(voxel[i]) || !sane(space_min[i], 1e12f) || !sane(space_max[i], 1e12f) || !sane(origin[i], 1e12f))
-            fastdiv = 0;
-    }
-    for (int i = 0; i < 9; i++) if (!sane(rot[i], 1e6f) || !sane(kinv[i], 1e6f)) fastdiv = 0;
-    P.trunc = trunc;
-    P.step = (float)((double)trunc * 0.05);
-    for (int i = 0; i < 9; i++) { P.rot.m[i] = rot[i]; P.kinv.m[i] = kinv[i]; }
-    P.width = width; P.height = height; P.table = d_table; P.occ = d_occ;
+    int rc = fill_params(P, d_dist, nx, ny, nz, voxel, space_min, space_max, trunc, origin, rot, kinv, width, height, d_table, &fastdiv);
+    if (rc) return rc;
+    P.occ = d_occ;
+    const BrickDims nb = brick_dims(nx, ny, nz);
+    P.nbx = nb.bx; P.nby = nb.by; P.nbz = nb.bz;
     P.vertices = d_vertices; P.khit = d_khit; P.n_samples = d_n_samples;
-
-    dim3 block(128);
-    dim3 grid((width + 15) / 16, (height + 7) / 8);
-    cudaStream_t s = (cudaStream_t)stream;
-    if (fastdiv) {
-        if (d_occ) raycast_kernel<true, true><<<grid, block, 0, s>>>(P);
-        else       raycast_kernel<true, false><<<grid, block, 0, s>>>(P);
-    } else {
-        if (d_occ) raycast_kernel<false, true><<<grid, block, 0, s>>>(P);
-        else       raycast_kernel<false, false><<<grid, block, 0, s>>>(P);
-    }
-    return (int)cudaGetLastError();
+    return launch_march<false>(P, fastdiv, (cudaStream_t)stream);
 }
 
 extern "C" int tsdf_b200_raycast(const float *d_dist, uint32_t nx, uint32_t ny, uint32_t nz,
@@ -376,6 +545,47 @@ extern "C" int tsdf_b200_raycast(const float *d_dist, uint32_t nx, uint32_t ny, 
     // IEEE division unless a caller (the level-2 volume) has proven the reciprocal form.
     return tsdf_b200_raycast_ex(d_dist, nx, ny, nz, voxel, space_min, space_max, trunc, origin, rot, kinv,
                                 width, height, d_table, d_occ, d_vertices, d_khit, d_n_samples, 0, stream);
+}
+
+extern "C" int tsdf_b200_raycast_slab(const float *d_dist_slab, uint32_t nx, uint32_t ny, uint32_t nz,
+                                      uint32_t z_base, uint32_t z_planes, uint32_t z_lo, uint32_t z_hi,
+                                      const float voxel[3], const float space_min[3], const float space_max[3],
+                                      float trunc, const float origin[3], const float rot[9], const float kinv[9],
+                                      uint32_t width, uint32_t height, const float *d_table,
+                                      const uint8_t *d_occ_slab, long long *d_keys,
+                                      unsigned long long *d_n_samples, int fastdiv, void *stream) {
+    if (!d_dist_slab || !d_keys) return TSDF_B200_EINVAL;
+    if (z_lo < z_base || z_hi > nz || z_lo > z_hi || z_base + z_planes > nz || z_planes == 0) return TSDF_B200_EINVAL;
+    // every cell starting in [z_lo, z_hi) needs planes l and min(l+1, nz-1)
+    if (z_hi > z_lo && (z_hi < nz ? z_hi : nz - 1) > z_base + z_planes - 1) return TSDF_B200_EINVAL;
+    if (d_occ_slab && z_base % TSDF_B200_BRICK != 0) return TSDF_B200_EINVAL;
+    RayParams P;
+    int rc = fill_params(P, d_dist_slab, nx, ny, nz, voxel, space_min, space_max, trunc, origin, rot, kinv, width, height, d_table, &fastdiv);
+    if (rc) return rc;
+    P.occ = d_occ_slab;
+    const BrickDims nb = brick_dims(nx, ny, z_planes);
+    P.nbx = nb.bx; P.nby = nb.by; P.nbz = nb.bz;
+    P.z_base = z_base; P.z_lo = z_lo; P.z_hi = z_hi;
+    P.keys = d_keys; P.n_samples = d_n_samples;
+    return launch_march<true>(P, fastdiv, (cudaStream_t)stream);
+}
+
+extern "C" int tsdf_b200_raycast_resolve(const long long *d_keys, const float space_min[3], const float space_max[3],
+                                         float trunc, const float origin[3], const float rot[9], const float kinv[9],
+                                         uint32_t width, uint32_t height, const float *d_table,
+                                         float *d_vertices, int32_t *d_khit, void *stream) {
+    if (!d_keys || !d_vertices) return TSDF_B200_EINVAL;
+    RayParams P;
+    int fastdiv = 0;
+    const float one[3] = { 1.f, 1.f, 1.f };
+    int rc = fill_params(P, nullptr, 1, 1, 1, one, space_min, space_max, trunc, origin, rot, kinv, width, height, d_table, &fastdiv);
+    if (rc) return rc;
+    P.keys = const_cast<long long *>(d_keys);
+    P.vertices = d_vertices; P.khit = d_khit;
+    dim3 block(128);
+    dim3 grid((width + 15) / 16, (height + 7) / 8);
+    resolve_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(P);
+    return (int)cudaGetLastError();
 }
 
 extern "C" int tsdf_b200_normals(uint32_t width, uint32_t height, const float *d_vertices, float *d_normals, void *stream) {

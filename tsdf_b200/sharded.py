@@ -21,6 +21,13 @@ from .capi import lib, check, fptr, fvec, colmajor, volume_params
 BRICK = 8
 
 
+def shard_ranges(nz, world, brick=BRICK):
+    """Z-slab [z0, z1) owned by each rank: whole 8-voxel bricks, in rank order."""
+    bricks = (nz + brick - 1) // brick
+    per = (bricks + world - 1) // world
+    return [(min(r * per * brick, nz), min((r + 1) * per * brick, nz)) for r in range(world)]
+
+
 def _ptr(t):
     return C.c_void_p(t.data_ptr()) if t is not None else None
 
@@ -36,13 +43,7 @@ class ShardedEngine:
         self.stream = C.c_void_p(stream if stream is not None else torch.cuda.current_stream().cuda_stream)
         self.skipping = skipping
         nz = self.n[2]
-        if world == 1:
-            self.z0, self.z1 = 0, nz
-        else:
-            bricks = (nz + BRICK - 1) // BRICK
-            per = (bricks + world - 1) // world
-            self.z0 = min(rank * per * BRICK, nz)
-            self.z1 = min((rank + 1) * per * BRICK, nz)
+        self.z0, self.z1 = shard_ranges(nz, world)[rank]
         self.zs1 = min(self.z1 + 1, nz) if world > 1 else nz        # stored planes [z0, zs1)
         planes = max(self.zs1 - self.z0, 1)
         nvl = self.n[0] * self.n[1] * planes
@@ -126,9 +127,9 @@ class ShardedEngine:
                                            self.stream), "raycast")
         else:
             import torch.distributed as dist
-            check(lib.tsdf_b200_raycast_slab(_ptr(self.dist), *self.n, self.z0, self.z0, self.z1, fptr(self.voxel),
-                                             fptr(smin), fptr(smax), self.trunc, origin_p, rot_p, kinv_p, w, h,
-                                             _ptr(self.table), occ, _ptr(self.keys), cnt, self.fastdiv, self.stream),
+            check(lib.tsdf_b200_raycast_slab(_ptr(self.dist), *self.n, self.z0, self.local_n[2], self.z0, self.z1,
+                                             fptr(self.voxel), fptr(smin), fptr(smax), self.trunc, origin_p, rot_p, kinv_p,
+                                             w, h, _ptr(self.table), occ, _ptr(self.keys), cnt, self.fastdiv, self.stream),
                   "raycast_slab")
             dist.all_reduce(self.keys, op=dist.ReduceOp.MIN)
             check(lib.tsdf_b200_raycast_resolve(_ptr(self.keys), fptr(smin), fptr(smax), self.trunc, origin_p, rot_p,

@@ -27,7 +27,8 @@ struct RayParams {
     M33 rot, kinv;
     uint32_t width, height;
     const float *table;
-    const uint8_t *occ;
+    const uint8_t *occ;          // per brick: a voxel of the brick or of its 1-voxel apron is outside the positive band
+    const uint8_t *occ_d;        // occ dilated by one brick (written by dilate_kernel right before the march)
     uint32_t nbx, nby, nbz;      // occupancy grid dimensions (local planes when sharded)
     float occ_lo, occ_hi;        // positive band
     uint32_t z_base, z_lo, z_hi; // Z-slab: global z of array plane 0; cells owned by this rank start in [z_lo, z_hi)
@@ -80,6 +81,23 @@ __device__ __forceinline__ bool near_far(const float o[3], const float d[3], con
     return can_intersect(smin[0], smax[0], o[0], d[0], near_t, far_t) &&
            can_intersect(smin[1], smax[1], o[1], d[1], near_t, far_t) &&
            can_intersect(smin[2], smax[2], o[2], d[2], near_t, far_t);
+}
+
+// occ_d[B] = OR of occ over the 27 bricks around B (missing neighbours count as empty: a sample that strays out
+// of the grid, or out of this rank's slab, is out of bounds or another rank's).
+__global__ void __launch_bounds__(256)
+dilate_kernel(const uint8_t *__restrict__ occ, uint8_t *__restrict__ occ_d, int nbx, int nby, int nbz) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y, z = blockIdx.z;
+    if (x >= nbx) return;
+    uint8_t any = 0;
+    for (int dz = -1; dz <= 1; dz++)
+        for (int dy = -1; dy <= 1; dy++)
+            for (int dx = -1; dx <= 1; dx++) {
+                const int xx = x + dx, yy = y + dy, zz = z + dz;
+                if (xx >= 0 && xx < nbx && yy >= 0 && yy < nby && zz >= 0 && zz < nbz)
+                    any |= occ[((size_t)zz * nby + yy) * nbx + xx];
+            }
+    occ_d[((size_t)z * nby + y) * nbx + x] = any;
 }
 
 // Per-ray set-up shared by the march and the resolve kernel: direction, clip, start point.
@@ -156,8 +174,8 @@ raycast_kernel(const __grid_constant__ RayParams P) {
             const float hi_adj[3] = { fsub(mx[0], fdiv(P.vs[0], 10.0f)), fsub(mx[1], fdiv(P.vs[1], 10.0f)), fsub(mx[2], fdiv(P.vs[2], 10.0f)) };
             const float inv_step = __frcp_rn(step);
             // Skipping helpers (approximate arithmetic, only ever used conservatively):
-            //   ainv = 1/|dir|, dt = parameter length of one brick, et = parameter length of the 2%-of-a-voxel guard band
-            float ainv[3], dtb[3], et[3];
+            //   ainv = 1/|dir|, dtb = parameter length of one brick
+            float ainv[3], dtb[3];
             int sgn[3];
             if (SKIP) {
 #pragma unroll
@@ -167,7 +185,6 @@ raycast_kernel(const __grid_constant__ RayParams P) {
                     ainv[a] = moving ? __frcp_rn(ad) : 0.0f;
                     sgn[a] = !moving ? 0 : (dir[a] > 0.0f ? 1 : -1);
                     dtb[a] = moving ? (float)TSDF_B200_BRICK * P.vs[a] * ainv[a] : 3.0e30f;
-                    et[a] = moving ? 0.02f * P.vs[a] * ainv[a] : 0.0f;
                 }
             }
 
@@ -221,65 +238,42 @@ raycast_kernel(const __grid_constant__ RayParams P) {
                                  (uint32_t)vox[0] >= P.nx || (uint32_t)vox[1] >= P.ny || (uint32_t)vox[2] >= P.nz;
 
                 // ---- level 1: runs of empty bricks ------------------------------------------------------
-                // A brick flag of 0 says every voxel of the brick and of its 1-voxel apron lies in the positive band,
-                // so any sample whose voxel is in the brick (and not in voxel layer 0, where the reference
-                // extrapolates, :87-99) is > 0.  From such a sample, walk the ray through consecutive empty bricks and
-                // jump to the last sample that is certainly still inside them.
-                if (SKIP && !oob && vox[0] >= 1 && vox[1] >= 1 && vox[2] >= 1) {
+                // occ_d[B] == 0 says: B and its 26 neighbours contain (with their 1-voxel aprons) only voxels in the
+                // positive band.  A sample's fp32 position is within ~1e-3 mm of the real line start + t*dir, i.e. in
+                // the brick the real line is in or in a neighbour of it, so while the real line runs through bricks
+                // with occ_d == 0 every sample on it is > 0 — no guard bands needed, grazing rays included.  Brick
+                // layer 0 of each axis is left to level 2 (the reference extrapolates in voxel layer 0, :87-99).
+                if (SKIP && !oob) {
                     int b[3] = { vox[0] / TSDF_B200_BRICK, vox[1] / TSDF_B200_BRICK, vox[2] / TSDF_B200_BRICK };
-                    const int bz_local = b[2] - (SLAB ? (int)(P.z_base / TSDF_B200_BRICK) : 0);
-                    const bool in_grid = !SLAB || (bz_local >= 0 && bz_local < (int)P.nbz);
+                    const int bz0 = SLAB ? (int)(P.z_base / TSDF_B200_BRICK) : 0;        // first brick layer held locally
+                    const int bz_local = b[2] - bz0;
+                    const bool in_grid = b[0] >= 1 && b[1] >= 1 && b[2] >= 1 && bz_local >= 0 && bz_local < (int)P.nbz;
                     long bi = ((long)bz_local * P.nby + b[1]) * P.nbx + b[0];
-                    if (in_grid && __ldg(P.occ + bi) == 0) {
-                        // distances (in t) to the exit faces of the landing brick; the landing point must be clear of
-                        // every face by the guard band, otherwise just step once (this sample is known positive)
-                        float tm[3];
-                        bool clear = true;
+                    if (in_grid && __ldg(P.occ_d + bi) == 0) {
+                        float tm[3];      // parameter distance from this sample to the exit face of the current brick
 #pragma unroll
                         for (int a = 0; a < 3; a++) {
-                            const float lo = ((b[a] == 0) ? 1.0f : (float)(b[a] * TSDF_B200_BRICK)) * P.vs[a];
+                            const float lo = (float)(b[a] * TSDF_B200_BRICK) * P.vs[a];
                             const float hi = (float)((b[a] + 1) * TSDF_B200_BRICK) * P.vs[a];
-                            const float dlo = p[a] - lo, dhi = hi - p[a];
-                            const float g = 0.02f * P.vs[a];
-                            clear = clear && dlo >= g && dhi >= g;
-                            tm[a] = sgn[a] > 0 ? dhi * ainv[a] : (sgn[a] < 0 ? dlo * ainv[a] : 1.0e30f);
+                            tm[a] = sgn[a] > 0 ? (hi - p[a]) * ainv[a] : (sgn[a] < 0 ? (p[a] - lo) * ainv[a] : 1.0e30f);
                         }
-                        int j = 0;
-                        if (clear) {
-                            const long stride[3] = { 1, (long)P.nbx, (long)P.nbx * P.nby };
-                            const int nb[3] = { (int)P.nbx, (int)P.nby, SLAB ? (int)P.nbz + (int)(P.z_base / TSDF_B200_BRICK) : (int)P.nbz };
-                            const int nb_lo_z = SLAB ? (int)(P.z_base / TSDF_B200_BRICK) : 0;
-                            for (int it = 0; it < 1024; it++) {
-                                const float tc = fminf(tm[0], fminf(tm[1], tm[2]));
-                                const int a = (tm[0] == tc) ? 0 : ((tm[1] == tc) ? 1 : 2);
-                                // the other two axes must be clear of their faces at the crossing (no corner grazing)
-                                bool ok = true;
-#pragma unroll
-                                for (int c = 0; c < 3; c++) {
-                                    const float rem = tm[c] - tc;
-                                    ok = ok && (c == a || (rem >= et[c] && rem <= dtb[c] - et[c]));
-                                }
-                                if (!ok) break;
-                                int nbk, lim_lo = 0, lim_hi, sg;
-                                long st;
-                                if (a == 0)      { nbk = b[0] + sgn[0]; lim_hi = nb[0]; sg = sgn[0]; st = stride[0]; }
-                                else if (a == 1) { nbk = b[1] + sgn[1]; lim_hi = nb[1]; sg = sgn[1]; st = stride[1]; }
-                                else             { nbk = b[2] + sgn[2]; lim_hi = nb[2]; sg = sgn[2]; st = stride[2]; lim_lo = nb_lo_z; }
-                                // never walk into brick layer 0 of an axis (the low-edge layer needs the voxel >= 1 test),
-                                // nor out of the grid / out of this rank's slab
-                                if (sg == 0 || nbk <= 0 || nbk < lim_lo || nbk >= lim_hi) break;
-                                const long nbi = bi + (sg > 0 ? st : -st);
-                                if (__ldg(P.occ + nbi) != 0) break;
-                                bi = nbi;
-                                if (a == 0)      { b[0] = nbk; tm[0] += dtb[0]; }
-                                else if (a == 1) { b[1] = nbk; tm[1] += dtb[1]; }
-                                else             { b[2] = nbk; tm[2] += dtb[2]; }
-                            }
-                            // exit of the last verified brick, pulled in by the guard band on every axis
-                            const float t_gain = fminf(tm[0] - et[0], fminf(tm[1] - et[1], tm[2] - et[2]));
-                            j = safe_steps(s_t, k, t, t_gain, inv_step);
+                        const long sx = sgn[0], sy = (long)sgn[1] * P.nbx, sz = (long)sgn[2] * P.nbx * P.nby;
+                        for (int it = 0; it < 4096; it++) {
+                            const float tc = fminf(tm[0], fminf(tm[1], tm[2]));
+                            if (!(tc < 1.0e29f)) break;
+                            int nbk; long nbi;
+                            const int a = (tm[0] == tc) ? 0 : ((tm[1] == tc) ? 1 : 2);
+                            if (a == 0)      { nbk = b[0] + sgn[0]; nbi = bi + sx; if (nbk < 1 || nbk >= (int)P.nbx) break; }
+                            else if (a == 1) { nbk = b[1] + sgn[1]; nbi = bi + sy; if (nbk < 1 || nbk >= (int)P.nby) break; }
+                            else             { nbk = b[2] + sgn[2]; nbi = bi + sz; if (nbk < 1 || nbk < bz0 || nbk >= bz0 + (int)P.nbz) break; }
+                            if (__ldg(P.occ_d + nbi) != 0) break;
+                            bi = nbi;
+                            if (a == 0)      { b[0] = nbk; tm[0] += dtb[0]; }
+                            else if (a == 1) { b[1] = nbk; tm[1] += dtb[1]; }
+                            else             { b[2] = nbk; tm[2] += dtb[2]; }
                         }
-                        k += 1 + j;
+                        const float t_gain = fminf(tm[0], fminf(tm[1], tm[2]));
+                        k += 1 + safe_steps(s_t, k, t, t_gain, inv_step);
                         continue;
                     }
                 }
@@ -498,7 +492,7 @@ static int fill_params(RayParams &P, const float *d_dist, uint32_t nx, uint32_t 
     P.step = (float)((double)trunc * 0.05);
     for (int i = 0; i < 9; i++) { P.rot.m[i] = rot[i]; P.kinv.m[i] = kinv[i]; }
     P.width = width; P.height = height; P.table = d_table;
-    P.occ = nullptr; P.nbx = P.nby = P.nbz = 0;
+    P.occ = nullptr; P.occ_d = nullptr; P.nbx = P.nby = P.nbz = 0;
     P.occ_lo = trunc * kOccLoFrac; P.occ_hi = trunc * kOccHiFrac;
     P.z_base = 0; P.z_lo = 0; P.z_hi = nz;
     P.vertices = nullptr; P.khit = nullptr; P.keys = nullptr; P.n_samples = nullptr;
@@ -506,7 +500,15 @@ static int fill_params(RayParams &P, const float *d_dist, uint32_t nx, uint32_t 
 }
 
 template <bool SLAB>
-static int launch_march(const RayParams &P, int fastdiv, cudaStream_t s) {
+static int launch_march(RayParams &P, int fastdiv, cudaStream_t s) {
+    if (P.occ) {
+        // the second half of the occupancy buffer is scratch for the dilated grid
+        const size_t nb = (size_t)P.nbx * P.nby * P.nbz;
+        uint8_t *occ_d = const_cast<uint8_t *>(P.occ) + nb;
+        if (P.nby > 65535 || P.nbz > 65535) return TSDF_B200_EINVAL;
+        dilate_kernel<<<dim3((P.nbx + 255) / 256, P.nby, P.nbz), 256, 0, s>>>(P.occ, occ_d, (int)P.nbx, (int)P.nby, (int)P.nbz);
+        P.occ_d = occ_d;
+    }
     dim3 block(128);
     dim3 grid((P.width + 15) / 16, (P.height + 7) / 8);
     if (fastdiv) {

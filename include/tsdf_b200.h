@@ -83,9 +83,9 @@ int tsdf_b200_integrate(float *d_dist, float *d_weight, const float *d_deform,
  * conventional K (same result bits, fewer instructions); on != 0 forces the general kernel.  */
 void tsdf_b200_debug_force_generic_integrate(int on);
 
-/* Size in bytes of the occupancy buffer of a volume: two bytes per 8^3 brick — the brick flags that
- * integrate / occupancy_rebuild maintain, followed by scratch for the dilated copy the raycast derives
- * from them on every call (so the raycast entry points WRITE the second half of d_occ).           */
+/* Size in bytes of the occupancy buffer of a volume: three bytes per 8^3 brick — the brick flags that
+ * integrate / occupancy_rebuild maintain, then the brick distance grid and a scratch copy that the
+ * raycast derives from the flags on every call (the raycast entry points WRITE those two thirds).  */
 size_t tsdf_b200_occupancy_bytes(uint32_t nx, uint32_t ny, uint32_t nz);
 
 /* Recompute the occupancy grid from scratch (after set_distance_data / file load). */

@@ -32,8 +32,8 @@ def test_host_only_entry_points(built):
     vox, trunc = capi.volume_params((100, 100, 100), (2000, 2000, 2000))
     assert vox.tolist() == [20.0, 20.0, 20.0]
     assert int(np.float32(trunc).view(np.uint32)) == 1108896677        # 38.10512, reference fixture
-    assert capi.lib.tsdf_b200_occupancy_bytes(512, 512, 512) == 2 * 64 ** 3
-    assert capi.lib.tsdf_b200_occupancy_bytes(100, 9, 1) == 2 * 13 * 2 * 1
+    assert capi.lib.tsdf_b200_occupancy_bytes(512, 512, 512) == 3 * 64 ** 3
+    assert capi.lib.tsdf_b200_occupancy_bytes(100, 9, 1) == 3 * 13 * 2 * 1
     # argument validation happens before any CUDA call
     assert capi.lib.tsdf_b200_integrate(None, None, None, 1, 1, 1, None, None, None, 1.0, None, None, None,
                                         1, 1, None, 0, 1, 0, None, None, None) == -1

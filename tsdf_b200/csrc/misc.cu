@@ -79,9 +79,10 @@ extern "C" int tsdf_b200_volume_params(uint32_t nx, uint32_t ny, uint32_t nz, co
 }
 
 extern "C" size_t tsdf_b200_occupancy_bytes(uint32_t nx, uint32_t ny, uint32_t nz) {
-    // first half: one flag per brick, maintained by integrate / rebuild; second half: raycast's dilated copy
+    // [brick flags, maintained by integrate / rebuild | brick distance grid | scratch]: the last two are
+    // rewritten by every raycast
     BrickDims nb = brick_dims(nx, ny, nz);
-    return 2 * (size_t)nb.bx * nb.by * nb.bz;
+    return 3 * (size_t)nb.bx * nb.by * nb.bz;
 }
 
 extern "C" int tsdf_b200_clear(float *d_dist, float *d_weight, uint32_t nx, uint32_t ny, uint32_t nz,

@@ -28,7 +28,7 @@ struct RayParams {
     uint32_t width, height;
     const float *table;
     const uint8_t *occ;          // per brick: a voxel of the brick or of its 1-voxel apron is outside the positive band
-    const uint8_t *occ_d;        // occ dilated by one brick (written by dilate_kernel right before the march)
+    const uint8_t *occ_d;        // brick distance grid (written by distance_pass_kernel right before the march)
     uint32_t nbx, nby, nbz;      // occupancy grid dimensions (local planes when sharded)
     float occ_lo, occ_hi;        // positive band
     uint32_t z_base, z_lo, z_hi; // Z-slab: global z of array plane 0; cells owned by this rank start in [z_lo, z_hi)
@@ -83,21 +83,29 @@ __device__ __forceinline__ bool near_far(const float o[3], const float d[3], con
            can_intersect(smin[2], smax[2], o[2], d[2], near_t, far_t);
 }
 
-// occ_d[B] = OR of occ over the 27 bricks around B (missing neighbours count as empty: a sample that strays out
-// of the grid, or out of this rank's slab, is out of bounds or another rank's).
+// Chebyshev distance transform of the brick flags, one separable pass per launch:
+//   out(B) = min over j in [-R, R] of max(in(B + j*axis), |j|)        (missing bricks count as empty)
+// with in = (flag ? 0 : R) for the first pass.  After the x, y and z passes out(B) is the distance, in bricks and
+// capped at R, from B to the nearest flagged brick (min-max over a cube separates because max distributes).
+constexpr int kDistCap = 16;
+template <int AXIS, bool FIRST>
 __global__ void __launch_bounds__(256)
-dilate_kernel(const uint8_t *__restrict__ occ, uint8_t *__restrict__ occ_d, int nbx, int nby, int nbz) {
+distance_pass_kernel(const uint8_t *__restrict__ in, uint8_t *__restrict__ out, int nbx, int nby, int nbz) {
     const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y, z = blockIdx.z;
     if (x >= nbx) return;
-    uint8_t any = 0;
-    for (int dz = -1; dz <= 1; dz++)
-        for (int dy = -1; dy <= 1; dy++)
-            for (int dx = -1; dx <= 1; dx++) {
-                const int xx = x + dx, yy = y + dy, zz = z + dz;
-                if (xx >= 0 && xx < nbx && yy >= 0 && yy < nby && zz >= 0 && zz < nbz)
-                    any |= occ[((size_t)zz * nby + yy) * nbx + xx];
-            }
-    occ_d[((size_t)z * nby + y) * nbx + x] = any;
+    const size_t stride = AXIS == 0 ? 1 : (AXIS == 1 ? (size_t)nbx : (size_t)nbx * nby);
+    const int pos = AXIS == 0 ? x : (AXIS == 1 ? y : z), len = AXIS == 0 ? nbx : (AXIS == 1 ? nby : nbz);
+    const size_t base = ((size_t)z * nby + y) * nbx + x;
+    auto value = [&](int j) -> int {
+        const uint8_t v = in[base + (ptrdiff_t)j * (ptrdiff_t)stride];
+        return FIRST ? (v ? 0 : kDistCap) : (int)v;
+    };
+    int best = value(0);
+    for (int j = 1; j < best; j++) {          // a candidate at offset j can only give max(.., j) >= j
+        if (pos - j >= 0)  best = min(best, max(value(-j), j));
+        if (pos + j < len) best = min(best, max(value(j), j));
+    }
+    out[base] = (uint8_t)best;
 }
 
 // Per-ray set-up shared by the march and the resolve kernel: direction, clip, start point.
@@ -237,44 +245,46 @@ raycast_kernel(const __grid_constant__ RayParams P) {
                 const bool oob = vox[0] < 0 || vox[1] < 0 || vox[2] < 0 ||
                                  (uint32_t)vox[0] >= P.nx || (uint32_t)vox[1] >= P.ny || (uint32_t)vox[2] >= P.nz;
 
-                // ---- level 1: runs of empty bricks ------------------------------------------------------
-                // occ_d[B] == 0 says: B and its 26 neighbours contain (with their 1-voxel aprons) only voxels in the
-                // positive band.  A sample's fp32 position is within ~1e-3 mm of the real line start + t*dir, i.e. in
-                // the brick the real line is in or in a neighbour of it, so while the real line runs through bricks
-                // with occ_d == 0 every sample on it is > 0 — no guard bands needed, grazing rays included.  Brick
-                // layer 0 of each axis is left to level 2 (the reference extrapolates in voxel layer 0, :87-99).
+                // ---- level 1: empty space, sphere-traced on the brick distance grid -----------------------------
+                // cd[B] = Chebyshev distance (in bricks, capped) from brick B to the nearest brick whose voxels or
+                // 1-voxel apron leave the positive band.  A sample's fp32 position is within ~1e-3 mm of the real
+                // line start + t*dir, i.e. in the brick the real line is in or in a face/edge/corner neighbour of it.
+                //   cd >= 2: while the real line stays within cd-2 bricks of B (per axis), every sample on it lies in
+                //            a brick at distance <= cd-1 of B, hence empty, hence > 0 — no guard band is needed and
+                //            rays grazing brick faces are handled like any other;
+                //   cd == 1: B itself is empty but a neighbour is not: skip to the exit of B pulled in by a guard
+                //            band (2% of a voxel, >> the rounding error of a sample position), provided the landing
+                //            point is itself clear of every face by that band.
+                // Voxel layer 0 of each axis is never skipped (the reference extrapolates there, :87-99): the landing
+                // point and every skipped sample keep 1.05 voxels away from the low faces of the volume.
                 if (SKIP && !oob) {
-                    int b[3] = { vox[0] / TSDF_B200_BRICK, vox[1] / TSDF_B200_BRICK, vox[2] / TSDF_B200_BRICK };
-                    const int bz0 = SLAB ? (int)(P.z_base / TSDF_B200_BRICK) : 0;        // first brick layer held locally
-                    const int bz_local = b[2] - bz0;
-                    const bool in_grid = b[0] >= 1 && b[1] >= 1 && b[2] >= 1 && bz_local >= 0 && bz_local < (int)P.nbz;
-                    long bi = ((long)bz_local * P.nby + b[1]) * P.nbx + b[0];
-                    if (in_grid && __ldg(P.occ_d + bi) == 0) {
-                        float tm[3];      // parameter distance from this sample to the exit face of the current brick
+                    const int b[3] = { vox[0] / TSDF_B200_BRICK, vox[1] / TSDF_B200_BRICK, vox[2] / TSDF_B200_BRICK };
+                    const int bz_local = b[2] - (SLAB ? (int)(P.z_base / TSDF_B200_BRICK) : 0);
+                    const bool in_grid = !SLAB || (bz_local >= 0 && bz_local < (int)P.nbz);
+                    const int cd = in_grid ? (int)__ldg(P.occ_d + ((size_t)bz_local * P.nby + b[1]) * P.nbx + b[0]) : 0;
+                    if (cd >= 1) {
+                        const float extra = (float)(cd - 2);      // whole bricks beyond the exit of B (cd >= 2)
+                        float t_gain = 3.0e30f;
+                        bool clear = true, off_low_edge = true;
 #pragma unroll
                         for (int a = 0; a < 3; a++) {
                             const float lo = (float)(b[a] * TSDF_B200_BRICK) * P.vs[a];
                             const float hi = (float)((b[a] + 1) * TSDF_B200_BRICK) * P.vs[a];
-                            tm[a] = sgn[a] > 0 ? (hi - p[a]) * ainv[a] : (sgn[a] < 0 ? (p[a] - lo) * ainv[a] : 1.0e30f);
+                            const float g = 0.02f * P.vs[a];
+                            const float dlo = p[a] - lo, dhi = hi - p[a];
+                            const float dedge = p[a] - 1.05f * P.vs[a];          // distance to the guarded low edge of the volume
+                            clear = clear && dlo >= g && dhi >= g;
+                            off_low_edge = off_low_edge && dedge >= 0.0f;
+                            float ta;
+                            if (cd >= 2) ta = (sgn[a] > 0 ? dhi : dlo) * ainv[a] + extra * dtb[a];
+                            else         ta = ((sgn[a] > 0 ? dhi : dlo) - g) * ainv[a];
+                            if (sgn[a] < 0) ta = fminf(ta, dedge * ainv[a]);
+                            if (sgn[a] != 0) t_gain = fminf(t_gain, ta);
                         }
-                        const long sx = sgn[0], sy = (long)sgn[1] * P.nbx, sz = (long)sgn[2] * P.nbx * P.nby;
-                        for (int it = 0; it < 4096; it++) {
-                            const float tc = fminf(tm[0], fminf(tm[1], tm[2]));
-                            if (!(tc < 1.0e29f)) break;
-                            int nbk; long nbi;
-                            const int a = (tm[0] == tc) ? 0 : ((tm[1] == tc) ? 1 : 2);
-                            if (a == 0)      { nbk = b[0] + sgn[0]; nbi = bi + sx; if (nbk < 1 || nbk >= (int)P.nbx) break; }
-                            else if (a == 1) { nbk = b[1] + sgn[1]; nbi = bi + sy; if (nbk < 1 || nbk >= (int)P.nby) break; }
-                            else             { nbk = b[2] + sgn[2]; nbi = bi + sz; if (nbk < 1 || nbk < bz0 || nbk >= bz0 + (int)P.nbz) break; }
-                            if (__ldg(P.occ_d + nbi) != 0) break;
-                            bi = nbi;
-                            if (a == 0)      { b[0] = nbk; tm[0] += dtb[0]; }
-                            else if (a == 1) { b[1] = nbk; tm[1] += dtb[1]; }
-                            else             { b[2] = nbk; tm[2] += dtb[2]; }
+                        if (off_low_edge && (cd >= 2 || clear)) {
+                            k += 1 + safe_steps(s_t, k, t, t_gain, inv_step);
+                            continue;
                         }
-                        const float t_gain = fminf(tm[0], fminf(tm[1], tm[2]));
-                        k += 1 + safe_steps(s_t, k, t, t_gain, inv_step);
-                        continue;
                     }
                 }
 
@@ -502,12 +512,15 @@ static int fill_params(RayParams &P, const float *d_dist, uint32_t nx, uint32_t 
 template <bool SLAB>
 static int launch_march(RayParams &P, int fastdiv, cudaStream_t s) {
     if (P.occ) {
-        // the second half of the occupancy buffer is scratch for the dilated grid
+        // occupancy buffer = [brick flags | distance grid | scratch], each one byte per brick
         const size_t nb = (size_t)P.nbx * P.nby * P.nbz;
-        uint8_t *occ_d = const_cast<uint8_t *>(P.occ) + nb;
+        uint8_t *cd = const_cast<uint8_t *>(P.occ) + nb, *tmp = cd + nb;
         if (P.nby > 65535 || P.nbz > 65535) return TSDF_B200_EINVAL;
-        dilate_kernel<<<dim3((P.nbx + 255) / 256, P.nby, P.nbz), 256, 0, s>>>(P.occ, occ_d, (int)P.nbx, (int)P.nby, (int)P.nbz);
-        P.occ_d = occ_d;
+        const dim3 g((P.nbx + 255) / 256, P.nby, P.nbz);
+        distance_pass_kernel<0, true><<<g, 256, 0, s>>>(P.occ, cd, (int)P.nbx, (int)P.nby, (int)P.nbz);
+        distance_pass_kernel<1, false><<<g, 256, 0, s>>>(cd, tmp, (int)P.nbx, (int)P.nby, (int)P.nbz);
+        distance_pass_kernel<2, false><<<g, 256, 0, s>>>(tmp, cd, (int)P.nbx, (int)P.nby, (int)P.nbz);
+        P.occ_d = cd;
     }
     dim3 block(128);
     dim3 grid((P.width + 15) / 16, (P.height + 7) / 8);

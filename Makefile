@@ -12,7 +12,7 @@ all: lib oracle
 
 lib: tsdf_b200/libtsdf_b200.so
 
-$(CSRC)/%.o: $(CSRC)/%.cu $(CSRC)/common.cuh include/tsdf_b200.h
+$(CSRC)/%.o: $(CSRC)/%.cu $(CSRC)/common.cuh $(CSRC)/integrate_rigid.cuh include/tsdf_b200.h
 	$(NVCC) $(NVCCFLAGS) -c $< -o $@
 
 tsdf_b200/libtsdf_b200.so: $(OBJS)

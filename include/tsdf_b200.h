@@ -63,12 +63,22 @@ int tsdf_b200_clear(float *d_dist, float *d_weight, uint32_t nx, uint32_t ny, ui
 int tsdf_b200_init_deformation(float *d_deform, uint32_t nx, uint32_t ny, uint32_t nz,
                                const float voxel[3], const float grid_offset[3], void *stream);
 
+/* Staged depth frame for tsdf_b200_integrate: a max-pyramid of the frame (largest depth per 2^l x 2^l pixel tile).
+ * The rigid-camera integrate kernel uses it to skip, per warp, slabs of voxels that lie entirely behind everything
+ * they can project onto (or entirely outside the image) without projecting them one by one.  Purely an
+ * acceleration structure: results are bit-identical with and without it.  d_staged holds
+ * tsdf_b200_depth_staged_bytes(width, height) bytes.  Replaces nothing in the reference, which projects every
+ * voxel of the volume for every frame (TSDF/TSDFVolume.cu:326-349).                                        */
+size_t tsdf_b200_depth_staged_bytes(uint32_t width, uint32_t height);
+int tsdf_b200_depth_stage(const uint16_t *d_depth, uint32_t width, uint32_t height, float *d_staged, void *stream);
+
 /* Replaces integrate_kernel (TSDF/TSDFVolume.cu:308-392) for planes z in [z_begin, z_end) of
  * the arrays.  The arrays hold nz planes whose plane 0 is global plane z_base of the volume
  * (0 for a whole volume; a Z-slab of a sharded volume otherwise; a multiple of 8 with d_occ).
  * d_deform == NULL selects the analytic identity grid: translation = ((v+0.5)*voxel) +
  * offset_at_clear, bit-identical to reading the array clear() wrote, without the 24 B/voxel
- * read.  d_occ (optional): occupancy bricks are marked for every voxel whose new distance
+ * read.  d_depth_staged (optional): the same frame after tsdf_b200_depth_stage (culling pyramid for the
+ * rigid-camera kernel).  d_occ (optional): occupancy bricks are marked for every voxel whose new distance
  * leaves the "certainly positive" band.  d_n_updated (optional): incremented by the number
  * of voxels rewritten (device counter, unsigned long long).                             */
 int tsdf_b200_integrate(float *d_dist, float *d_weight, const float *d_deform,
@@ -76,6 +86,7 @@ int tsdf_b200_integrate(float *d_dist, float *d_weight, const float *d_deform,
                         const float offset_at_clear[3], const float offset[3], float trunc,
                         const float inv_pose[16], const float k[9], const float kinv[9],
                         uint32_t width, uint32_t height, const uint16_t *d_depth,
+                        const float *d_depth_staged,
                         uint32_t z_begin, uint32_t z_end, uint32_t z_base, uint8_t *d_occ,
                         unsigned long long *d_n_updated, void *stream);
 

@@ -41,14 +41,18 @@ class DeviceVolume:
             check(lib.tsdf_b200_init_deformation(ptr(self.deform), *self.n, fptr(self.voxel), fptr(self.offset_at_clear), None))
         torch.cuda.synchronize()
 
-    def integrate(self, depth, inv_pose, k, kinv, z_begin=0, z_end=None, count=True):
+    def integrate(self, depth, inv_pose, k, kinv, z_begin=0, z_end=None, count=True, staged=True):
         h, w = depth.shape
         d = depth if isinstance(depth, torch.Tensor) else dev(depth)
         z_end = self.n[2] if z_end is None else z_end
         self.counter[0] = 0
+        st = None
+        if staged:
+            st = torch.empty((lib.tsdf_b200_depth_staged_bytes(w, h) + 3) // 4, dtype=torch.float32, device="cuda")
+            check(lib.tsdf_b200_depth_stage(ptr(d), w, h, ptr(st), None), "depth_stage")
         check(lib.tsdf_b200_integrate(ptr(self.dist), ptr(self.weight), ptr(self.deform), *self.n, fptr(self.voxel),
                                       fptr(self.offset_at_clear), fptr(self.offset), self.trunc, fptr(colmajor(inv_pose)),
-                                      fptr(colmajor(k)), fptr(colmajor(kinv)), w, h, ptr(d), z_begin, z_end, 0, ptr(self.occ),
+                                      fptr(colmajor(k)), fptr(colmajor(kinv)), w, h, ptr(d), ptr(st), z_begin, z_end, 0, ptr(self.occ),
                                       C.c_void_p(self.counter.data_ptr()) if count else None, None), "integrate")
         torch.cuda.synchronize()
         return int(self.counter[0].item())

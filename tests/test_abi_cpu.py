@@ -36,7 +36,7 @@ def test_host_only_entry_points(built):
     assert capi.lib.tsdf_b200_occupancy_bytes(100, 9, 1) == 3 * 13 * 2 * 1
     # argument validation happens before any CUDA call
     assert capi.lib.tsdf_b200_integrate(None, None, None, 1, 1, 1, None, None, None, 1.0, None, None, None,
-                                        1, 1, None, 0, 1, 0, None, None, None) == -1
+                                        1, 1, None, None, 0, 1, 0, None, None, None) == -1
     assert capi.lib.tsdf_b200_normals(0, 0, None, None, None) == -1
 
 

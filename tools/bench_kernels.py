@@ -27,7 +27,7 @@ for f in [int(x) for x in args.frames.split(",")]:
     ti, tr = [], []
     for r in range(args.reps):
         e = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
-        e[0].record(); eng.integrate(d, cam); e[1].record(); eng.raycast(W, H, cam); e[2].record()
+        e[0].record(); eng.integrate(d, cam, restage=False); e[1].record(); eng.raycast(W, H, cam); e[2].record()
         torch.cuda.synchronize()
         ti.append(e[0].elapsed_time(e[1])); tr.append(e[1].elapsed_time(e[2]))
     ns = eng.raycast(W, H, cam, count=True)

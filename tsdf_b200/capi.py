@@ -26,8 +26,10 @@ SIGNATURES = {
     "tsdf_b200_volume_params": (C.c_int, [_u32, _u32, _u32, _f, _f, _f]),
     "tsdf_b200_clear": (C.c_int, [_vp, _vp, _u32, _u32, _u32, C.c_float, _vp, _vp]),
     "tsdf_b200_init_deformation": (C.c_int, [_vp, _u32, _u32, _u32, _f, _f, _vp]),
+    "tsdf_b200_depth_staged_bytes": (C.c_size_t, [_u32, _u32]),
+    "tsdf_b200_depth_stage": (C.c_int, [_vp, _u32, _u32, _vp, _vp]),
     "tsdf_b200_integrate": (C.c_int, [_vp, _vp, _vp, _u32, _u32, _u32, _f, _f, _f, C.c_float, _f, _f, _f,
-                                      _u32, _u32, _vp, _u32, _u32, _u32, _vp, _vp, _vp]),
+                                      _u32, _u32, _vp, _vp, _u32, _u32, _u32, _vp, _vp, _vp]),
     "tsdf_b200_debug_force_generic_integrate": (None, [C.c_int]),
     "tsdf_b200_occupancy_bytes": (C.c_size_t, [_u32, _u32, _u32]),
     "tsdf_b200_occupancy_rebuild": (C.c_int, [_vp, _u32, _u32, _u32, C.c_float, _vp, _vp]),

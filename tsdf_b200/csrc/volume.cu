@@ -28,6 +28,7 @@ struct tsdf_b200_volume {
     uint8_t *d_occ = nullptr;
     float *d_table = nullptr;
     uint16_t *d_depth = nullptr; size_t depth_cap = 0;
+    float *d_staged = nullptr; size_t staged_cap = 0;   // staged depth frame (tsdf_b200_depth_stage)
     float *d_vn = nullptr; size_t pix_cap = 0;   // vertices then normals
     unsigned long long *d_counters = nullptr;    // [0] voxels rewritten, [1] samples
     unsigned long long h_counters[2] = {0, 0};
@@ -41,11 +42,11 @@ size_t nvox(const tsdf_b200_volume *v) { return (size_t)v->nx * v->ny * v->nz; }
 
 void release(tsdf_b200_volume *v) {
     cudaFree(v->d_dist); cudaFree(v->d_weight); cudaFree(v->d_deform); cudaFree(v->d_occ);
-    cudaFree(v->d_table); cudaFree(v->d_depth); cudaFree(v->d_vn); cudaFree(v->d_counters);
+    cudaFree(v->d_table); cudaFree(v->d_depth); cudaFree(v->d_staged); cudaFree(v->d_vn); cudaFree(v->d_counters);
     free(v->h_colour);
     if (v->stream) cudaStreamDestroy(v->stream);
     v->d_dist = v->d_weight = v->d_deform = nullptr; v->d_occ = nullptr; v->d_table = nullptr;
-    v->d_depth = nullptr; v->d_vn = nullptr; v->d_counters = nullptr; v->h_colour = nullptr; v->stream = nullptr;
+    v->d_depth = nullptr; v->d_staged = nullptr; v->d_vn = nullptr; v->d_counters = nullptr; v->h_colour = nullptr; v->stream = nullptr;
 }
 
 int allocate(tsdf_b200_volume *v, uint32_t nx, uint32_t ny, uint32_t nz, float px, float py, float pz) {
@@ -198,11 +199,20 @@ extern "C" int tsdf_b200_volume_integrate(tsdf_b200_volume *v, const uint16_t *h
         TSDF_CUDA_TRY(cudaMalloc(&v->d_depth, npix * sizeof(uint16_t)));
         v->depth_cap = npix;
     }
+    const size_t staged_bytes = tsdf_b200_depth_staged_bytes(width, height);
+    if (staged_bytes > v->staged_cap) {
+        // (the texture object the library caches for the old buffer is dropped when its address is reused)
+        cudaFree(v->d_staged); v->d_staged = nullptr; v->staged_cap = 0;
+        TSDF_CUDA_TRY(cudaMalloc(&v->d_staged, staged_bytes));
+        v->staged_cap = staged_bytes;
+    }
     TSDF_CUDA_TRY(cudaMemcpyAsync(v->d_depth, host_depth, npix * sizeof(uint16_t), cudaMemcpyHostToDevice, v->stream));
+    int rc = tsdf_b200_depth_stage(v->d_depth, width, height, v->d_staged, v->stream);
+    if (rc) return rc;
     if (v->counting) TSDF_CUDA_TRY(cudaMemsetAsync(v->d_counters, 0, sizeof(unsigned long long), v->stream));
     const float *deform = v->deform_identity ? nullptr : v->d_deform;
-    int rc = tsdf_b200_integrate(v->d_dist, v->d_weight, deform, v->nx, v->ny, v->nz, v->vs, v->off_clear, v->off, v->trunc,
-                                 inv_pose, k, kinv, width, height, v->d_depth, 0, v->nz, 0, v->d_occ,
+    rc = tsdf_b200_integrate(v->d_dist, v->d_weight, deform, v->nx, v->ny, v->nz, v->vs, v->off_clear, v->off, v->trunc,
+                                 inv_pose, k, kinv, width, height, v->d_depth, v->d_staged, 0, v->nz, 0, v->d_occ,
                                  v->counting ? v->d_counters : nullptr, v->stream);
     if (rc) return rc;
     if (v->counting)

@@ -33,7 +33,7 @@ def _ptr(t):
 
 
 class ShardedEngine:
-    def __init__(self, n, physical, rank=0, world=1, stream=None, skipping=True):
+    def __init__(self, n, physical, rank=0, world=1, stream=None, skipping=True, stage_depth=True):
         self.n = tuple(int(x) for x in n)
         self.physical = fvec(physical)
         self.rank, self.world = rank, world
@@ -42,6 +42,8 @@ class ShardedEngine:
         self.offset_at_clear = np.zeros(3, np.float32)
         self.stream = C.c_void_p(stream if stream is not None else torch.cuda.current_stream().cuda_stream)
         self.skipping = skipping
+        self.stage_depth = stage_depth
+        self._staged = None
         nz = self.n[2]
         self.z0, self.z1 = shard_ranges(nz, world)[rank]
         self.zs1 = min(self.z1 + 1, nz) if world > 1 else nz        # stored planes [z0, zs1)
@@ -62,8 +64,9 @@ class ShardedEngine:
             if bad.value:
                 self.fastdiv = 0
         self.clear()
-        # kernels per step: integrate + raycast + normals (+ resolve when sharded; the all-reduce is NCCL's)
-        self.launches_per_step = 3 if world == 1 else 5
+        # kernels per step: 2 pyramid launches (depth staging) + integrate (+ halo integrate when sharded) + 3
+        # brick-distance passes + raycast + normals (+ resolve when sharded; the all-reduce is NCCL's)
+        self.launches_per_step = (6 if world == 1 else 8) + (2 if stage_depth else 0)
 
     # ------------------------------------------------------------------------------------------
     def clear(self):
@@ -89,23 +92,37 @@ class ShardedEngine:
             cam._cabi = m
         return m
 
-    def integrate(self, d_depth, cam, count=False):
-        """d_depth: (H, W) uint16 CUDA tensor.  Returns voxels rewritten (owned planes only) when count."""
+    def stage(self, d_depth):
+        """Build the culling pyramid of a depth frame (tsdf_b200_depth_stage); integrate() does it unless restage=False."""
+        h, w = d_depth.shape
+        need = lib.tsdf_b200_depth_staged_bytes(w, h)
+        if self._staged is None or self._staged.numel() * 4 < need:
+            self._staged = torch.empty((need + 3) // 4, dtype=torch.float32, device="cuda")
+        check(lib.tsdf_b200_depth_stage(_ptr(d_depth), w, h, _ptr(self._staged), self.stream), "depth_stage")
+
+    def integrate(self, d_depth, cam, count=False, restage=True):
+        """d_depth: (H, W) uint16 CUDA tensor.  Returns voxels rewritten (owned planes only) when count.
+        restage=False reuses the staged frame of the previous call (same depth frame; kernel-timing aid)."""
         h, w = d_depth.shape
         if count:
             self.counters[0] = 0
         mats = self._mats(cam)[:3]
         own, stored = self.z1 - self.z0, self.zs1 - self.z0
+        staged = None
+        if self.stage_depth:
+            if restage:
+                self.stage(d_depth)
+            staged = _ptr(self._staged)
         if own > 0:
             check(lib.tsdf_b200_integrate(_ptr(self.dist), _ptr(self.weight), None, *self.local_n, fptr(self.voxel),
                                           fptr(self.offset_at_clear), fptr(self.offset), self.trunc, *mats,
-                                          w, h, _ptr(d_depth), 0, own, self.z0, _ptr(self.occ),
+                                          w, h, _ptr(d_depth), staged, 0, own, self.z0, _ptr(self.occ),
                                           C.c_void_p(self.counters.data_ptr()) if count else None, self.stream),
                   "integrate")
         if stored > own:      # redundant halo plane, not counted
             check(lib.tsdf_b200_integrate(_ptr(self.dist), _ptr(self.weight), None, *self.local_n, fptr(self.voxel),
                                           fptr(self.offset_at_clear), fptr(self.offset), self.trunc, *mats,
-                                          w, h, _ptr(d_depth), own, stored, self.z0, _ptr(self.occ), None, self.stream),
+                                          w, h, _ptr(d_depth), staged, own, stored, self.z0, _ptr(self.occ), None, self.stream),
                   "integrate halo")
         if count:
             return int(self.counters[0].item())

@@ -153,6 +153,20 @@ int tsdf_b200_raycast_resolve(const long long *d_keys, const float space_min[3],
 int tsdf_b200_normals(uint32_t width, uint32_t height, const float *d_vertices,
                       float *d_normals, void *stream);
 
+/* Replaces extract_surface_ms: get_cube_contribution + host prefix sum + generate_vertices
+ * (MarchingCubes/MarkAndSweepMC.cu:132-153, 456-473, 218-304, 390-497).  d_dist holds nz_planes planes starting at
+ * global plane z_base; cubes whose base plane is in [cz_begin, cz_end) (local, clamped to nz_planes - 1) are
+ * processed — a whole volume is (0, 0, nz - 1); a Z-shard passes its owned planes and relies on its halo plane.
+ * *d_vertices_out receives a cudaMalloc'ed array of 3 floats per vertex (nullptr when empty; release it with
+ * tsdf_b200_device_free), in the reference's order: ascending cube index (x fastest), triangle-table order within
+ * a cube, three consecutive vertices per triangle.  Synchronises `stream`.                                   */
+int tsdf_b200_mc_extract(const float *d_dist, uint32_t nx, uint32_t ny, uint32_t nz_planes, uint32_t z_base,
+                         uint32_t cz_begin, uint32_t cz_end, const float voxel[3], const float offset[3],
+                         float **d_vertices_out, unsigned long long *n_vertices_out, void *stream);
+void tsdf_b200_device_free(void *d_ptr);
+/* cudaMemcpy device -> host for callers that do not link the CUDA runtime themselves. */
+int tsdf_b200_copy_to_host(void *host, const void *device, size_t bytes);
+
 /* Exhaustive check (every numerator bit pattern with 2^-100 <= |a| <= 2^100, and +-0) that the
  * 3-instruction reciprocal division used by the raycast kernel equals IEEE a/divisor.  *mismatches is a
  * host pointer.  The level-2 volume runs this once per voxel size and falls back to

@@ -15,7 +15,9 @@ LIB_PATH = os.path.join(_DIR, "liboracle.so")
 
 def build(force=False):
     src = os.path.join(_DIR, "tsdf_oracle.c")
-    if force or not os.path.exists(LIB_PATH) or os.path.getmtime(LIB_PATH) < os.path.getmtime(src):
+    tables = os.path.join(_DIR, "..", "tsdf_b200", "csrc", "mc_tables.h")
+    newest = max(os.path.getmtime(src), os.path.getmtime(tables))
+    if force or not os.path.exists(LIB_PATH) or os.path.getmtime(LIB_PATH) < newest:
         subprocess.check_call(["gcc", "-O2", "-ffp-contract=off", "-fno-fast-math", "-fopenmp", "-fPIC", "-shared",
                                "-Wall", "-o", LIB_PATH, src, "-lm"])
     return LIB_PATH
@@ -43,6 +45,8 @@ _lib.oracle_resolve.restype = None
 _lib.oracle_resolve.argtypes = [_vp, _f, _f, C.c_float, _f, _f, _f, _u32, _u32, _vp, _vp]
 _lib.oracle_normals.restype = None
 _lib.oracle_normals.argtypes = [_u32, _u32, _vp, _vp]
+_lib.oracle_mc_extract.restype = C.c_uint64
+_lib.oracle_mc_extract.argtypes = [_vp, _u32, _u32, _u32, _f, _f, _vp]
 _lib.oracle_hit_voxels.restype = None
 _lib.oracle_hit_voxels.argtypes = [_u32, _vp, _f, _f, _u32, _u32, _vp]
 
@@ -160,4 +164,16 @@ def hit_voxels(vertices, space_min, voxel, nx, ny):
     out = np.empty(vertices.shape[0], np.int64)
     _lib.oracle_hit_voxels(vertices.shape[0], vertices.ctypes.data, _fp(_fv(space_min)), _fp(_fv(voxel)), nx, ny,
                            out.ctypes.data)
+    return out
+
+
+def mc_extract(dist, n, voxel, offset):
+    """Marching cubes of a host distance array (x fastest): (n_vertices, 3) float32 in the reference's order."""
+    dist = np.ascontiguousarray(dist, np.float32)
+    vox, off = _fv(voxel), _fv(offset)
+    count = _lib.oracle_mc_extract(dist.ctypes.data, n[0], n[1], n[2], _fp(vox), _fp(off), None)
+    out = np.empty((count, 3), np.float32)
+    if count:
+        got = _lib.oracle_mc_extract(dist.ctypes.data, n[0], n[1], n[2], _fp(vox), _fp(off), out.ctypes.data)
+        assert got == count
     return out

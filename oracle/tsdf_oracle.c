@@ -459,3 +459,50 @@ void oracle_hit_voxels(uint32_t n_pix, const float *vertices, const float space_
         out[i] = x + y * (int64_t)nx + z * (int64_t)nx * ny;
     }
 }
+
+/* ---- marching cubes -------------------------------------------------------------------------
+ * Restatement of extract_surface_ms (reference src/MarchingCubes/MarkAndSweepMC.cu): cube corner numbering
+ * voxel_indices_for_cube_index :60-100, calculate_cube_type :110-124, per-cube vertex count :132-153, host
+ * scan in ascending cube index :456-473, generate_vertices :218-304 with interpolate :44-58 and
+ * centre_of_voxel_at (TSDF/TSDF_utilities.cu:10-17).  Triangle table: Bourke's, shared with the product
+ * (tsdf_b200/csrc/mc_tables.h) and checked against the reference's copy by tests/test_mc_cpu.py.
+ * Two passes: out == NULL counts, otherwise fills 3 floats per vertex.  Returns the vertex count.    */
+#include "../tsdf_b200/csrc/mc_tables.h"
+
+uint64_t oracle_mc_extract(const float *dist, uint32_t nx, uint32_t ny, uint32_t nz, const float voxel[3],
+                           const float offset[3], float *out) {
+    uint64_t n_out = 0;
+    if (nx < 2 || ny < 2 || nz < 2) return 0;
+    for (uint32_t z = 0; z + 1 < nz; z++)
+        for (uint32_t y = 0; y + 1 < ny; y++)
+            for (uint32_t x = 0; x + 1 < nx; x++) {
+                /* corners 0..7: (x,z+1) (x+1,z+1) (x+1,z) (x,z) on plane y, then the same on y+1 */
+                const uint32_t cx[8] = { x, x + 1, x + 1, x, x, x + 1, x + 1, x };
+                const uint32_t cy[8] = { y, y, y, y, y + 1, y + 1, y + 1, y + 1 };
+                const uint32_t cz[8] = { z + 1, z + 1, z, z, z + 1, z + 1, z, z };
+                float w[8];
+                unsigned type = 0;
+                for (int c = 0; c < 8; c++) {
+                    w[c] = dist[((size_t)nx * ny) * cz[c] + (size_t)nx * cy[c] + cx[c]];
+                    if (w[c] < 0) type |= 1u << c;
+                }
+                const char *tri = kMcTriangles[type];
+                if (!tri[0]) continue;
+                if (!out) { n_out += strlen(tri); continue; }
+                for (int i = 0; tri[i]; i++) {
+                    const int e = tri[i] <= '9' ? tri[i] - '0' : tri[i] - 'a' + 10;
+                    int a = kMcEdgeCorners[e][0], b = kMcEdgeCorners[e][1];
+                    float w0 = w[a], w1 = w[b];
+                    if (w0 > 0 && w1 < 0) { const float t = w0; w0 = w1; w1 = t; const int ti = a; a = b; b = ti; }
+                    const float va[3] = { (cx[a] + 0.5f) * voxel[0] + offset[0], (cy[a] + 0.5f) * voxel[1] + offset[1], (cz[a] + 0.5f) * voxel[2] + offset[2] };
+                    const float vb[3] = { (cx[b] + 0.5f) * voxel[0] + offset[0], (cy[b] + 0.5f) * voxel[1] + offset[1], (cz[b] + 0.5f) * voxel[2] + offset[2] };
+                    const float ratio = -(w0) / (w1 - w0);
+                    for (int k = 0; k < 3; k++) {
+                        const float delta = vb[k] - va[k];
+                        out[3 * n_out + k] = va[k] + delta * ratio;
+                    }
+                    n_out++;
+                }
+            }
+    return n_out;
+}

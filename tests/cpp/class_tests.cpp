@@ -1,0 +1,322 @@
+// class_tests.cpp — known-answer tests of the drop-in C++ class layer (tsdf_b200/include + tsdf_b200/host).
+//
+// Camera: the runnable known-answer tests of the reference's src/Tests/TestTSDF/Test_Camera.cpp, restated without
+// gtest (world_to_camera for six facings :35-146 and three translations :148-197, the (-1,-1,-1) look :199-221, pixel /
+// image-plane round trips at the four corners :244-323, pose bookkeeping :327-353, look_at against the axis rotations of
+// TestHelpers.cpp:103-143 :355-476, set_pose :480-493).  Not restated: givenPointWhenInCentreOfImageThenCamPointIsOrigin
+// (:225-240) — it expects pixel (320,240) to be the principal point, which the default camera (331, 234.6) makes false in
+// the reference itself — and the test that needs the author's TUM dataset (:497-520).
+// PNG / DepthImage / TUMDataLoader / PLY: round trips through the zlib codec and the TUM directory layout.
+// With --gpu: TSDFVolume / GPURaycaster / extract_surface through the classes (the -m gpu tests run that part).
+//
+// Exit code 0 = all checks passed; failures are listed on stderr.
+#include "../../tsdf_b200/include/TSDFVolume.hpp"
+#include "../../tsdf_b200/include/GPURaycaster.hpp"
+#include "../../tsdf_b200/include/MarkAndSweepMC.hpp"
+#include "../../tsdf_b200/include/TUMDataLoader.hpp"
+#include "../../tsdf_b200/include/PngWrapper.hpp"
+#include "../../tsdf_b200/include/PngUtilities.hpp"
+#include "../../tsdf_b200/include/RenderUtilities.hpp"
+#include "../../tsdf_b200/include/Definitions.hpp"
+#include "../../tsdf_b200/include/ply.hpp"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <fstream>
+#include <memory>
+#include <sstream>
+#include <string>
+#include <sys/stat.h>
+#include <vector>
+
+static int g_failures = 0, g_checks = 0;
+#define CHECK(cond) do { g_checks++; if (!(cond)) { g_failures++; std::fprintf(stderr, "FAIL %s:%d: %s\n", __FILE__, __LINE__, #cond); } } while (0)
+#define CHECK_NEAR(a, b, eps) do { g_checks++; const double a_ = (a), b_ = (b); if (!(std::fabs(a_ - b_) <= (eps))) { g_failures++; \
+    std::fprintf(stderr, "FAIL %s:%d: %s = %.9g, expected %.9g\n", __FILE__, __LINE__, #a, a_, b_); } } while (0)
+
+using Eigen::Matrix4f;
+using Eigen::Vector2f;
+using Eigen::Vector2i;
+using Eigen::Vector3f;
+
+static const float EPS = 1e-6f;
+static const Vector3f kWorld[8] = { Vector3f{0, 0, 0}, Vector3f{100, 0, 0}, Vector3f{100, 100, 0}, Vector3f{0, 100, 0},
+                                    Vector3f{0, 100, 100}, Vector3f{0, 0, 100}, Vector3f{100, 0, 100}, Vector3f{100, 100, 100} };
+
+// Expected camera coordinate = sign/permutation of the world coordinate, after an optional translation.
+static void check_facing(const char *name, float lx, float ly, float lz, bool look, const int perm[3], const float sign[3]) {
+    std::unique_ptr<Camera> cam(Camera::default_depth_camera());
+    if (look) cam->look_at(lx, ly, lz);
+    for (int i = 0; i < 8; i++) {
+        const Vector3f c = cam->world_to_camera(kWorld[i]);
+        for (int a = 0; a < 3; a++) {
+            g_checks++;
+            const float want = sign[a] * kWorld[i][perm[a]];
+            if (!(std::fabs(c[a] - want) <= EPS)) { g_failures++; std::fprintf(stderr, "FAIL facing %s point %d axis %d: %g vs %g\n", name, i, a, c[a], want); }
+        }
+    }
+}
+
+static Matrix4f y_rotation(float theta, const Vector3f &pos) {
+    Matrix4f r;
+    r << std::cos(theta), 0, std::sin(theta), pos.x(), 0, 1, 0, pos.y(), -std::sin(theta), 0, std::cos(theta), pos.z(), 0, 0, 0, 1;
+    return r;
+}
+static Matrix4f x_rotation(float theta, const Vector3f &pos) {
+    Matrix4f r;
+    r << 1, 0, 0, pos.x(), 0, std::cos(theta), -std::sin(theta), pos.y(), 0, std::sin(theta), std::cos(theta), pos.z(), 0, 0, 0, 1;
+    return r;
+}
+static void check_look(const Vector3f &from, const Matrix4f &expected) {
+    std::unique_ptr<Camera> cam(Camera::default_depth_camera());
+    cam->move_to(from);
+    cam->look_at(Vector3f::Zero());
+    for (int i = 0; i < 16; i++) CHECK_NEAR(cam->pose()(i), expected(i), EPS);
+}
+
+static void camera_tests() {
+    { const int p[3] = {0, 1, 2}; const float s[3] = {1, 1, 1};   check_facing("+z (default)", 0, 0, 0, false, p, s); }
+    { const int p[3] = {2, 1, 0}; const float s[3] = {1, 1, -1};  check_facing("-x", -1, 0, 0, true, p, s); }
+    { const int p[3] = {0, 2, 1}; const float s[3] = {1, 1, -1};  check_facing("-y", 0, -1, 0, true, p, s); }
+    { const int p[3] = {0, 2, 1}; const float s[3] = {1, -1, 1};  check_facing("+y", 0, 1, 0, true, p, s); }
+    { const int p[3] = {2, 1, 0}; const float s[3] = {-1, 1, 1};  check_facing("+x", 1, 0, 0, true, p, s); }
+    { const int p[3] = {0, 1, 2}; const float s[3] = {-1, 1, -1}; check_facing("-z", 0, 0, -1, true, p, s); }
+    for (int axis = 0; axis < 3; axis++) {                 // translations: camera = world - position
+        std::unique_ptr<Camera> cam(Camera::default_depth_camera());
+        cam->move_to(axis == 0 ? 100.f : 0.f, axis == 1 ? 100.f : 0.f, axis == 2 ? 100.f : 0.f);
+        for (int i = 0; i < 8; i++) {
+            const Vector3f c = cam->world_to_camera(kWorld[i]);
+            for (int a = 0; a < 3; a++) CHECK_NEAR(c[a], kWorld[i][a] - (a == axis ? 100.f : 0.f), EPS);
+        }
+    }
+    {   // at (-1,-1,-1) looking at the origin: the origin is sqrt(3) ahead on the optical axis.  (The reference test expects
+        // -sqrt(2) for z, :216-218 — a known-bad expectation; the geometry is checked here instead.)
+        std::unique_ptr<Camera> cam(Camera::default_depth_camera());
+        cam->move_to(-1, -1, -1);
+        cam->look_at(0, 0, 0);
+        const Vector3f c = cam->world_to_camera(Vector3f{0, 0, 0});
+        CHECK_NEAR(c.x(), 0, EPS); CHECK_NEAR(c.y(), 0, EPS); CHECK_NEAR(c.z(), std::sqrt(3.0), 1e-5);
+    }
+    const int corners[4][2] = { {0, 0}, {640, 0}, {0, 480}, {640, 480} };
+    for (const auto &px : corners) {                       // pixel -> image plane -> pixel
+        std::unique_ptr<Camera> cam(Camera::default_depth_camera());
+        const Vector2i start{px[0], px[1]};
+        const Vector2f plane = cam->pixel_to_image_plane(start);
+        CHECK_NEAR(plane.x(), px[0] ? 0.5 : -0.5, 0.1);
+        CHECK_NEAR(plane.y(), px[1] ? 0.5 : -0.5, 0.11);
+        const Vector2i back = cam->image_plane_to_pixel(plane);
+        CHECK(back.x() == start.x() && back.y() == start.y());
+    }
+    {
+        std::unique_ptr<Camera> cam(Camera::default_depth_camera());
+        CHECK(cam->pose() == Matrix4f::Identity());
+        cam->move_to(Vector3f{100.0f, 200.0f, 300.0f});
+        CHECK(cam->pose()(0, 3) == 100 && cam->pose()(1, 3) == 200 && cam->pose()(2, 3) == 300);
+        const Vector3f where = cam->position();
+        CHECK(where.x() == 100 && where.y() == 200 && where.z() == 300);
+    }
+    check_look(Vector3f{0, 0, 100}, y_rotation(-(float)M_PI, Vector3f{0, 0, 100}));
+    check_look(Vector3f{100, 0, 0}, y_rotation(-(float)M_PI_2, Vector3f{100, 0, 0}));
+    check_look(Vector3f{-100, 0, 0}, y_rotation((float)M_PI_2, Vector3f{-100, 0, 0}));
+    check_look(Vector3f{0, 0, -100}, y_rotation(0, Vector3f{0, 0, -100}));
+    check_look(Vector3f{0, 100, 0}, x_rotation((float)M_PI_2, Vector3f{0, 100, 0}));
+    check_look(Vector3f{0, -100, 0}, x_rotation(-(float)M_PI_2, Vector3f{0, -100, 0}));
+    {
+        std::unique_ptr<Camera> cam(Camera::default_depth_camera());
+        Matrix4f pose;
+        pose << 0, 0, 1, 10, 0, 1, 0, 20, -1, 0, 0, 30, 0, 0, 0, 1;
+        cam->set_pose(pose);
+        CHECK(cam->pose() == pose);
+        const Matrix4f product = cam->pose() * cam->inverse_pose();
+        for (int i = 0; i < 16; i++) CHECK_NEAR(product(i), Matrix4f::Identity()(i), 1e-5);
+        const Eigen::Matrix3f kk = cam->k() * cam->kinv();
+        for (int i = 0; i < 9; i++) CHECK_NEAR(kk(i), Eigen::Matrix3f::Identity()(i), 1e-5);
+        // world -> pixel of a point on the optical axis is the principal point
+        cam->set_pose(Matrix4f::Identity());
+        const Vector2i centre = cam->world_to_pixel(Vector3f{0, 0, 1000});
+        CHECK(centre.x() == 331 && centre.y() == 235);
+        // camera_to_world inverts world_to_camera
+        cam->set_pose(pose);
+        const Vector3f there = cam->camera_to_world(cam->world_to_camera(Vector3f{12, -7, 3}));
+        CHECK_NEAR(there.x(), 12, 1e-4); CHECK_NEAR(there.y(), -7, 1e-4); CHECK_NEAR(there.z(), 3, 1e-4);
+    }
+    {   // depth map -> vertices + normals: a fronto-parallel plane has normal (0,0,-1)... in the (right x below) convention +z
+        std::unique_ptr<Camera> cam(Camera::default_depth_camera());
+        const uint32_t w = 8, h = 6;
+        std::vector<uint16_t> depth(w * h, 1000);
+        depth[0] = 0;
+        Eigen::Matrix<float, 3, Eigen::Dynamic> v, n;
+        cam->depth_image_to_vertices_and_normals(depth.data(), w, h, v, n);
+        CHECK(v.cols() == (Eigen::Index)(w * h) && n.cols() == (Eigen::Index)(w * h));
+        CHECK(v(0, 0) == BAD_VERTEX[0] && n(0, 0) == 0 && n(1, 0) == 0 && n(2, 0) == 0);
+        const int i = 2 * w + 3;
+        CHECK_NEAR(v(2, i), 1000, 1e-3);
+        CHECK_NEAR(n(0, i), 0, 1e-5); CHECK_NEAR(n(1, i), 0, 1e-5); CHECK_NEAR(std::fabs(n(2, i)), 1, 1e-5);
+        CHECK(n(2, (h - 1) * w + 2) == 0);               // last row: no neighbour below
+    }
+}
+
+static std::string g_tmp;
+
+static void io_tests() {
+    // 16-bit PNG round trip (big-endian samples in the file), then through DepthImage
+    const uint32_t w = 37, h = 11;
+    std::vector<uint16_t> px(w * h);
+    for (uint32_t i = 0; i < w * h; i++) px[i] = static_cast<uint16_t>((i * 2654435761u) >> 16);
+    const std::string p16 = g_tmp + "/d16.png";
+    CHECK(save_png_to_file(p16, w, h, px.data()));
+    uint32_t rw = 0, rh = 0;
+    std::unique_ptr<uint16_t[]> back(load_png_from_file(p16, rw, rh));
+    CHECK(back && rw == w && rh == h && std::memcmp(back.get(), px.data(), px.size() * 2) == 0);
+    {
+        std::ifstream f(p16, std::ios::binary);
+        unsigned char sig[8];
+        f.read(reinterpret_cast<char *>(sig), 8);
+        CHECK(sig[0] == 0x89 && sig[1] == 'P' && sig[2] == 'N' && sig[3] == 'G');
+    }
+    DepthImage img(p16);
+    CHECK(img.width() == w && img.height() == h && img.data()[5] == px[5]);
+    uint16_t mn = 1, mx = 0;
+    img.min_max(mn, mx);
+    uint16_t emn = 0xffff, emx = 0;
+    for (uint16_t v : px) { emn = std::min(emn, v); emx = std::max(emx, v); }
+    CHECK(mn == emn && mx == emx);
+    img.scale_depth(0.2f);
+    CHECK(img.data()[7] == static_cast<uint16_t>(static_cast<float>(px[7]) * 0.2f));
+    img.truncate_depth_to(3000);
+    for (uint32_t i = 0; i < w * h; i++) CHECK(img.data()[i] <= 3000);
+    // colour + 8-bit through PngWrapper
+    std::vector<uint8_t> rgb(w * h * 3);
+    for (size_t i = 0; i < rgb.size(); i++) rgb[i] = static_cast<uint8_t>(i * 7);
+    PngWrapper colour(static_cast<uint16_t>(w), static_cast<uint16_t>(h), rgb.data(), PngWrapper::COLOUR);
+    CHECK(colour.save_to(g_tmp + "/c.png"));
+    PngWrapper reread(g_tmp + "/c.png", PngWrapper::COLOUR);
+    CHECK(reread.width() == w && reread.height() == h);
+    std::unique_ptr<uint8_t[]> rgb_back(load_colour_png_from_file(g_tmp + "/c.png", rw, rh));
+    CHECK(rgb_back && std::memcmp(rgb_back.get(), rgb.data(), rgb.size()) == 0);
+    PngWrapper grey(static_cast<uint16_t>(w), static_cast<uint16_t>(h), rgb.data(), PngWrapper::GREYSCALE_8);
+    CHECK(grey.save_to(g_tmp + "/g.png"));
+    bool threw = false;
+    try { PngWrapper missing(g_tmp + "/nope.png"); } catch (const std::invalid_argument &) { threw = true; }
+    CHECK(threw);
+
+    // TUM directory: ground_truth.txt + depth/<stamp>.png, 5000 units per metre, translation metres -> mm
+    mkdir((g_tmp + "/tum").c_str(), 0755);
+    mkdir((g_tmp + "/tum/depth").c_str(), 0755);
+    std::vector<uint16_t> frame(w * h, 5000);             // 1 m
+    frame[3] = 0;
+    CHECK(save_png_to_file(g_tmp + "/tum/depth/1.5.png", w, h, frame.data()));
+    {
+        std::ofstream gt(g_tmp + "/tum/ground_truth.txt");
+        gt << "# timestamp tx ty tz qx qy qz qw\n1.5 0.1 0.2 0.3 0 0 0 1\n2.5 0 0 0 0 0.7071068 0 0.7071068\n";
+    }
+    TUMDataLoader loader(g_tmp + "/tum");
+    Matrix4f pose;
+    std::unique_ptr<DepthImage> first(loader.next(pose));
+    CHECK(first && first->data()[0] == 1000 && first->data()[3] == 0);
+    CHECK_NEAR(pose(0, 3), 100, 1e-3); CHECK_NEAR(pose(1, 3), 200, 1e-3); CHECK_NEAR(pose(2, 3), 300, 1e-3);
+    CHECK_NEAR(pose(0, 0), 1, EPS); CHECK_NEAR(pose(1, 1), 1, EPS); CHECK_NEAR(pose(2, 2), 1, EPS); CHECK(pose(3, 3) == 1);
+    std::unique_ptr<DepthImage> second(loader.next(pose));       // its file does not exist
+    CHECK(!second);
+    std::unique_ptr<DepthImage> third(loader.next(pose));
+    CHECK(!third);
+    threw = false;
+    try { TUMDataLoader nothing(g_tmp + "/not-there"); } catch (const std::invalid_argument &) { threw = true; }
+    CHECK(threw);
+
+    // PLY
+    std::vector<float3> verts = { float3{0, 0, 0}, float3{1, 0, 0}, float3{0, 1, 0} };
+    std::vector<int3> tris = { int3{0, 2, 1} };
+    write_to_ply(g_tmp + "/m.ply", verts, tris);
+    std::ifstream ply(g_tmp + "/m.ply");
+    std::stringstream all;
+    all << ply.rdbuf();
+    CHECK(all.str().find("element vertex 3") != std::string::npos && all.str().find("3 0 2 1") != std::string::npos);
+
+    // renderers: NaN vertices (no surface) shade to the ambient level, normals map to [0,255]
+    Eigen::Matrix<float, 3, Eigen::Dynamic> v, n;
+    v.resize(3, 4); n.resize(3, 4);
+    for (int i = 0; i < 4; i++) { v(0, i) = 0; v(1, i) = 0; v(2, i) = 10; n(0, i) = 0; n(1, i) = 0; n(2, i) = -1; }
+    v(0, 3) = NAN;
+    std::unique_ptr<Camera> cam(Camera::default_depth_camera());
+    std::unique_ptr<PngWrapper> scene(scene_as_png(2, 2, v, n, *cam, Vector3f{0, 0, 0}));
+    std::unique_ptr<PngWrapper> normals(normals_as_png(2, 2, n));
+    CHECK(scene && scene->width() == 2 && normals && normals->height() == 2);
+}
+
+// ---- with a GPU: the volume, the raycaster and marching cubes through the classes ------------------------------
+static void gpu_tests() {
+    bool threw = false;
+    try { TSDFVolume bad(TSDFVolume::UInt3{0, 4, 4}, TSDFVolume::Float3{1, 1, 1}); } catch (const std::invalid_argument &) { threw = true; }
+    CHECK(threw);
+    TSDFVolume volume(TSDFVolume::UInt3{64, 64, 64}, TSDFVolume::Float3{3000.0f, 3000.0f, 3000.0f});
+    CHECK(volume.size().x == 64 && volume.physical_size().z == 3000.0f);
+    CHECK_NEAR(volume.voxel_size().x, 46.875, 1e-6);
+    CHECK_NEAR(volume.truncation_distance(), 1.1f * std::sqrt(3.0f * 46.875f * 46.875f), 1e-3);
+    CHECK(volume.index(1, 2, 3) == 1 + 2 * 64 + 3 * 64 * 64);
+    CHECK(volume.distance_data() != nullptr && volume.weight_data() != nullptr);
+
+    // a wall at z = 2000 mm seen from a camera at (1500, 1500, -1000) looking down +z
+    std::unique_ptr<Camera> cam(Camera::default_depth_camera());
+    cam->move_to(1500, 1500, -1000);
+    std::vector<uint16_t> depth(640 * 480, 3000);
+    for (int f = 0; f < 3; f++) volume.integrate(depth.data(), 640, 480, *cam);
+
+    Eigen::Matrix<float, 3, Eigen::Dynamic> vertices, normals;
+    volume.raycast(640, 480, *cam, vertices, normals);
+    CHECK(vertices.cols() == 640 * 480 && normals.cols() == 640 * 480);
+    const int centre = 240 * 640 + 320;
+    CHECK_NEAR(vertices(2, centre), 2000, volume.voxel_size().z);          // the wall, to within a voxel
+    CHECK_NEAR(normals(2, centre), -1, 1e-3);                              // facing the camera (v1 x v2 convention)
+    size_t hits = 0;
+    for (int i = 0; i < 640 * 480; i++) hits += vertices(0, i) == vertices(0, i);
+    CHECK(hits > 100000);
+
+    GPURaycaster raycaster(320, 240);
+    std::unique_ptr<DepthImage> rendered(raycaster.render_to_depth_image(volume, *cam));
+    CHECK(rendered && rendered->width() == 320 && rendered->height() == 240);
+
+    std::vector<float3> mesh_vertices;
+    std::vector<int3> triangles;
+    extract_surface(&volume, mesh_vertices, triangles);
+    CHECK(!mesh_vertices.empty() && mesh_vertices.size() == triangles.size() * 3);
+    CHECK(triangles[0].x == 0 && triangles[0].y == 2 && triangles[0].z == 1);
+    // two sheets: the wall's zero crossing, and the sign change where the fused band (down to -trunc behind the wall)
+    // meets voxels no frame ever touched (still +trunc) — marching cubes does not look at weights, in the reference either
+    float zmin = 1e30f, zmax = -1e30f;
+    for (const float3 &v : mesh_vertices) { zmin = std::min(zmin, v.z); zmax = std::max(zmax, v.z); }
+    CHECK_NEAR(zmin, 2000, volume.voxel_size().z);
+    CHECK(zmax <= 2000 + volume.truncation_distance() + 2 * volume.voxel_size().z);
+
+    // save / load round trip through the reference's file format
+    const std::string path = g_tmp + "/wall.tsdf";
+    CHECK(volume.save_to_file(path));
+    TSDFVolume loaded(path);
+    CHECK(loaded.size().y == 64 && loaded.truncation_distance() == volume.truncation_distance());
+    Eigen::Matrix<float, 3, Eigen::Dynamic> v2, n2;
+    loaded.raycast(640, 480, *cam, v2, n2);
+    CHECK(std::memcmp(v2.data(), vertices.data(), sizeof(float) * 3 * 640 * 480) == 0);
+    CHECK(!loaded.load_from_file(path));                                    // a stub in the reference too
+
+    volume.clear();
+    volume.raycast(64, 48, *cam, vertices, normals);
+    hits = 0;
+    for (int i = 0; i < 64 * 48; i++) hits += vertices(0, i) == vertices(0, i);
+    CHECK(hits == 0);
+}
+
+int main(int argc, char **argv) {
+    bool gpu = false;
+    g_tmp = "/tmp";
+    for (int i = 1; i < argc; i++) {
+        if (std::string(argv[i]) == "--gpu") gpu = true;
+        else g_tmp = argv[i];
+    }
+    camera_tests();
+    io_tests();
+    if (gpu) gpu_tests();
+    std::printf("%d checks, %d failures%s\n", g_checks, g_failures, gpu ? " (with GPU part)" : "");
+    return g_failures ? 1 : 0;
+}

@@ -1,0 +1,237 @@
+// mc.cu — iso-surface extraction (marching cubes) for sm_100a.
+//
+// Replaces get_cube_contribution + the host-side prefix sum + generate_vertices of the reference
+// (src/MarchingCubes/MarkAndSweepMC.cu:132-153, 456-473, 218-304).  Same output contract: one vertex per triangle-table
+// entry, cubes in ascending cube index (x fastest over an (nx-1)(ny-1)(nz-1) grid), three consecutive vertices per
+// triangle; same arithmetic per vertex (voxel centres (i+0.5)*voxel + offset, interpolate() :44-58, no FMA).  What is
+// different is where the work happens: the reference copies one byte per cube to the host, scans them serially and
+// copies cube lists back; here nothing but the vertex count crosses the bus — per-block counts, an exclusive scan of the
+// block counts, and a second pass that recomputes each cube's count (cheaper than storing 134 MB of them at 512^3),
+// scans inside the block and writes the vertices in place.
+#include "common.cuh"
+#include "mc_tables.h"
+
+namespace tsdf {
+
+constexpr int kMcBlock = 256;
+
+__constant__ unsigned char c_mc_count[256];          // vertices per cube type
+__constant__ unsigned char c_mc_tri[256][16];        // edge numbers, 0xff-terminated
+__constant__ unsigned char c_mc_edge[12][2];         // corner pair of each edge
+
+struct McParams {
+    const float *dist;
+    uint32_t nx, ny, nz;         // planes held by the array
+    uint32_t cz_begin, cz_end;   // cube base planes processed (local)
+    uint32_t z_base;             // global plane of local plane 0 (Z-slab of a sharded volume)
+    float vs[3], off[3];
+    uint32_t cubes_x, cubes_y;   // nx - 1, ny - 1
+    unsigned long long n_cubes;  // cubes_x * cubes_y * (cz_end - cz_begin)
+};
+
+// corner c of the cube based at voxel (x, y, z): reference numbering (MarkAndSweepMC.cu:60-100)
+__device__ __forceinline__ void corner_voxel(int c, uint32_t x, uint32_t y, uint32_t z, uint32_t &vx, uint32_t &vy, uint32_t &vz) {
+    vx = x + (((c & 3) == 1 || (c & 3) == 2) ? 1u : 0u);
+    vy = y + ((c & 4) ? 1u : 0u);
+    vz = z + (((c & 3) == 0 || (c & 3) == 1) ? 1u : 0u);
+}
+
+__device__ __forceinline__ bool cube_of(const McParams &P, unsigned long long i, uint32_t &x, uint32_t &y, uint32_t &z) {
+    if (i >= P.n_cubes) return false;
+    const unsigned long long slab = (unsigned long long)P.cubes_x * P.cubes_y;
+    z = (uint32_t)(i / slab) + P.cz_begin;
+    const uint32_t r = (uint32_t)(i % slab);
+    y = r / P.cubes_x;
+    x = r % P.cubes_x;
+    return true;
+}
+
+__device__ __forceinline__ uint32_t cube_type_at(const McParams &P, uint32_t x, uint32_t y, uint32_t z, float w[8]) {
+    uint32_t type = 0;
+#pragma unroll
+    for (int c = 0; c < 8; c++) {
+        uint32_t vx, vy, vz;
+        corner_voxel(c, x, y, z, vx, vy, vz);
+        w[c] = __ldg(P.dist + ((size_t)P.nx * P.ny) * vz + (size_t)P.nx * vy + vx);
+        type |= (w[c] < 0 ? 1u : 0u) << c;               // calculate_cube_type (:110-124)
+    }
+    return type;
+}
+
+__device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t *s_warp, uint32_t &block_total) {
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= (uint32_t)o) inc += t;
+    }
+    if (lane == 31) s_warp[warp] = inc;
+    __syncthreads();
+    uint32_t base = 0, total = 0;
+    for (int i = 0; i < kMcBlock / 32; i++) {
+        if ((uint32_t)i < warp) base += s_warp[i];
+        total += s_warp[i];
+    }
+    __syncthreads();
+    block_total = total;
+    return base + inc - v;
+}
+
+// pass 1: vertices contributed by each block of kMcBlock consecutive cubes
+__global__ void __launch_bounds__(kMcBlock)
+mc_count_kernel(const __grid_constant__ McParams P, uint32_t *__restrict__ block_counts) {
+    __shared__ uint32_t s_warp[kMcBlock / 32];
+    uint32_t x, y, z, n = 0;
+    float w[8];
+    if (cube_of(P, (unsigned long long)blockIdx.x * kMcBlock + threadIdx.x, x, y, z)) n = c_mc_count[cube_type_at(P, x, y, z, w)];
+    uint32_t total;
+    block_exclusive_scan(n, s_warp, total);
+    if (threadIdx.x == 0) block_counts[blockIdx.x] = total;
+}
+
+// pass 2: exclusive scan of the block counts (one block; a few hundred thousand entries at 512^3)
+__global__ void __launch_bounds__(1024)
+mc_scan_kernel(const uint32_t *__restrict__ block_counts, unsigned long long *__restrict__ block_offsets, uint32_t n_blocks,
+               unsigned long long *total_out) {
+    __shared__ unsigned long long s_part[1024];
+    const uint32_t per = (n_blocks + 1023) / 1024;
+    const uint32_t b = threadIdx.x * per, e = min(b + per, n_blocks);
+    unsigned long long sum = 0;
+    for (uint32_t i = b; i < e; i++) sum += block_counts[i];
+    s_part[threadIdx.x] = sum;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned long long run = 0;
+        for (int i = 0; i < 1024; i++) { const unsigned long long t = s_part[i]; s_part[i] = run; run += t; }
+        *total_out = run;
+    }
+    __syncthreads();
+    unsigned long long run = s_part[threadIdx.x];
+    for (uint32_t i = b; i < e; i++) { block_offsets[i] = run; run += block_counts[i]; }
+}
+
+// interpolate (MarkAndSweepMC.cu:44-58) for one coordinate set
+__device__ __forceinline__ void mc_interpolate(const float v0[3], const float v1[3], float w0, float w1, float out[3]) {
+    const float *a = v0, *b = v1;
+    if (w0 > 0 && w1 < 0) { const float t = w0; w0 = w1; w1 = t; a = v1; b = v0; }
+    const float ratio = fdiv(-w0, fsub(w1, w0));
+#pragma unroll
+    for (int i = 0; i < 3; i++) out[i] = fadd(fmul(fsub(b[i], a[i]), ratio), a[i]);
+}
+
+// pass 3: vertices
+__global__ void __launch_bounds__(kMcBlock)
+mc_generate_kernel(const __grid_constant__ McParams P, const unsigned long long *__restrict__ block_offsets, float *__restrict__ vertices) {
+    __shared__ uint32_t s_warp[kMcBlock / 32];
+    uint32_t x = 0, y = 0, z = 0, n = 0, type = 0;
+    float w[8];
+    if (cube_of(P, (unsigned long long)blockIdx.x * kMcBlock + threadIdx.x, x, y, z)) {
+        type = cube_type_at(P, x, y, z, w);
+        n = c_mc_count[type];
+    }
+    uint32_t total;
+    const uint32_t local = block_exclusive_scan(n, s_warp, total);
+    if (n == 0) return;
+    float *out = vertices + 3 * (block_offsets[blockIdx.x] + local);
+    // voxel centres of the 8 corners: centre_of_voxel_at (TSDF_utilities.cu:10-17) with the volume's offset
+    float c[8][3];
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        uint32_t vx, vy, vz;
+        corner_voxel(k, x, y, z, vx, vy, vz);
+        c[k][0] = fadd(fmul(fadd((float)(int)vx, 0.5f), P.vs[0]), P.off[0]);
+        c[k][1] = fadd(fmul(fadd((float)(int)vy, 0.5f), P.vs[1]), P.off[1]);
+        c[k][2] = fadd(fmul(fadd((float)(int)(vz + P.z_base), 0.5f), P.vs[2]), P.off[2]);
+    }
+    for (uint32_t i = 0; i < n; i++) {
+        const int e = c_mc_tri[type][i];
+        const int a = c_mc_edge[e][0], b = c_mc_edge[e][1];
+        float v[3];
+        mc_interpolate(c[a], c[b], w[a], w[b], v);
+        out[3 * i + 0] = v[0]; out[3 * i + 1] = v[1]; out[3 * i + 2] = v[2];
+    }
+}
+
+}  // namespace tsdf
+
+using namespace tsdf;
+
+static int upload_tables() {
+    static bool done[64] = { false };
+    int dev = 0;
+    TSDF_CUDA_TRY(cudaGetDevice(&dev));
+    if (dev < 64 && done[dev]) return 0;
+    unsigned char count[256], tri[256][16];
+    for (int t = 0; t < 256; t++) {
+        const char *s = kMcTriangles[t];
+        int n = 0;
+        for (; s[n]; n++) tri[t][n] = (unsigned char)(s[n] <= '9' ? s[n] - '0' : s[n] - 'a' + 10);
+        count[t] = (unsigned char)n;
+        for (; n < 16; n++) tri[t][n] = 0xff;
+    }
+    TSDF_CUDA_TRY(cudaMemcpyToSymbol(c_mc_count, count, sizeof(count)));
+    TSDF_CUDA_TRY(cudaMemcpyToSymbol(c_mc_tri, tri, sizeof(tri)));
+    TSDF_CUDA_TRY(cudaMemcpyToSymbol(c_mc_edge, kMcEdgeCorners, sizeof(kMcEdgeCorners)));
+    if (dev < 64) done[dev] = true;
+    return 0;
+}
+
+extern "C" int tsdf_b200_mc_extract(const float *d_dist, uint32_t nx, uint32_t ny, uint32_t nz_planes, uint32_t z_base,
+                                    uint32_t cz_begin, uint32_t cz_end, const float voxel[3], const float offset[3],
+                                    float **d_vertices_out, unsigned long long *n_vertices_out, void *stream) {
+    if (!d_dist || !voxel || !offset || !d_vertices_out || !n_vertices_out) return TSDF_B200_EINVAL;
+    *d_vertices_out = nullptr;
+    *n_vertices_out = 0;
+    if (nx == 0 || ny == 0 || nz_planes == 0) return TSDF_B200_EINVAL;
+    if (cz_end > nz_planes - 1) cz_end = nz_planes - 1;            // a cube needs plane z + 1
+    if (nx < 2 || ny < 2 || cz_begin >= cz_end) return 0;
+    int rc = upload_tables();
+    if (rc) return rc;
+    cudaStream_t s = (cudaStream_t)stream;
+    McParams P;
+    P.dist = d_dist; P.nx = nx; P.ny = ny; P.nz = nz_planes;
+    P.cz_begin = cz_begin; P.cz_end = cz_end; P.z_base = z_base;
+    for (int i = 0; i < 3; i++) { P.vs[i] = voxel[i]; P.off[i] = offset[i]; }
+    P.cubes_x = nx - 1; P.cubes_y = ny - 1;
+    P.n_cubes = (unsigned long long)P.cubes_x * P.cubes_y * (cz_end - cz_begin);
+    const unsigned long long n_blocks64 = (P.n_cubes + kMcBlock - 1) / kMcBlock;
+    if (n_blocks64 > 0x7fffffffull) return TSDF_B200_EINVAL;
+    const uint32_t n_blocks = (uint32_t)n_blocks64;
+
+    uint32_t *d_counts = nullptr;
+    unsigned long long *d_offsets = nullptr, *d_total = nullptr;
+    float *d_vertices = nullptr;
+    unsigned long long total = 0;
+    cudaError_t e = cudaMalloc(&d_counts, (size_t)n_blocks * sizeof(uint32_t));
+    if (e == cudaSuccess) e = cudaMalloc(&d_offsets, ((size_t)n_blocks + 1) * sizeof(unsigned long long));
+    if (e == cudaSuccess) {
+        d_total = d_offsets + n_blocks;
+        mc_count_kernel<<<n_blocks, kMcBlock, 0, s>>>(P, d_counts);
+        mc_scan_kernel<<<1, 1024, 0, s>>>(d_counts, d_offsets, n_blocks, d_total);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(&total, d_total, sizeof(total), cudaMemcpyDeviceToHost, s);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+    if (e == cudaSuccess && total > 0) {
+        e = cudaMalloc(&d_vertices, (size_t)total * 3 * sizeof(float));
+        if (e == cudaSuccess) {
+            mc_generate_kernel<<<n_blocks, kMcBlock, 0, s>>>(P, d_offsets, d_vertices);
+            e = cudaGetLastError();
+        }
+        if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+    }
+    cudaFree(d_counts);
+    cudaFree(d_offsets);
+    if (e != cudaSuccess) { cudaFree(d_vertices); return (int)e; }
+    *d_vertices_out = d_vertices;
+    *n_vertices_out = total;
+    return 0;
+}
+
+extern "C" void tsdf_b200_device_free(void *d_ptr) { cudaFree(d_ptr); }
+
+extern "C" int tsdf_b200_copy_to_host(void *host, const void *device, size_t bytes) {
+    if ((!host || !device) && bytes) return TSDF_B200_EINVAL;
+    return (int)cudaMemcpy(host, device, bytes, cudaMemcpyDeviceToHost);
+}

@@ -167,6 +167,19 @@ void tsdf_b200_device_free(void *d_ptr);
 /* cudaMemcpy device -> host for callers that do not link the CUDA runtime themselves. */
 int tsdf_b200_copy_to_host(void *host, const void *device, size_t bytes);
 
+/* Replaces BilateralFilter::filter_bpp (BilateralFilter.cpp:53-121), which is host code in the reference.  kernel:
+ * kernel_size^2 spatial weights, similarity: n_similarity range weights — the look-up tables the reference's
+ * constructor builds (:15-42); the caller computes them on the host so that the device evaluates no transcendental
+ * and the result equals the host loop bit for bit.  d_out != d_in.  8-bit: the reference exactly; 16-bit: the
+ * reference is undefined behaviour there (see csrc/bilateral.cu), the table may cover all 65536 differences.    */
+int tsdf_b200_bilateral_u8(const uint8_t *d_in, uint8_t *d_out, uint32_t width, uint32_t height, const float *d_kernel,
+                           uint32_t kernel_size, const float *d_similarity, uint32_t n_similarity, void *stream);
+int tsdf_b200_bilateral_u16(const uint16_t *d_in, uint16_t *d_out, uint32_t width, uint32_t height, const float *d_kernel,
+                            uint32_t kernel_size, const float *d_similarity, uint32_t n_similarity, void *stream);
+/* In-place filtering of a HOST image (bits_per_pixel 8 or 16) with HOST tables: BilateralFilter::filter. */
+int tsdf_b200_bilateral_host(void *host_image, int bits_per_pixel, uint32_t width, uint32_t height, const float *host_kernel,
+                             uint32_t kernel_size, const float *host_similarity, uint32_t n_similarity);
+
 /* Exhaustive check (every numerator bit pattern with 2^-100 <= |a| <= 2^100, and +-0) that the
  * 3-instruction reciprocal division used by the raycast kernel equals IEEE a/divisor.  *mismatches is a
  * host pointer.  The level-2 volume runs this once per voxel size and falls back to

@@ -23,7 +23,7 @@ OUT="$HERE/_ref"
 [ -d "$REF" ] || { echo "reference sources not found at $REF; keeping prebuilt oracle/_ref"; exit 0; }
 if [ -f "$OUT/libref_cuda_O3.so" ] && [ -f "$OUT/libref_cuda_G.so" ] && \
    [ "$OUT/libref_cuda_O3.so" -nt "$HERE/ref_harness.cu" ] && [ "$OUT/libref_cuda_O3.so" -nt "$HERE/build_ref.sh" ] && \
-   [ "$OUT/libref_cuda_O3.so" -nt "$HERE/../tsdf_b200/compat/eigen_compat.hpp" ]; then
+   [ "$OUT/libref_cuda_O3.so" -nt "$HERE/../tsdf_b200/compat/eigen_compat.hpp" ] && [ -f "$OUT/libref_bilateral.so" ]; then
     exit 0
 fi
 mkdir -p "$OUT/build"
@@ -53,5 +53,8 @@ build() {   # $1 = tag, rest = flags
 }
 build O3 -Xcompiler -O0 -fmad=false -lineinfo
 build G -Xcompiler -O0 -G
+# The reference's host-side bilateral filter (src/BilateralFilter.cpp, standalone C++): pins oracle_bilateral for 8-bit images.
+g++ -O2 -std=c++11 -fPIC -shared -ffp-contract=off -include cstdint -include cstddef -I"$REF" -o "$OUT/libref_bilateral.so" \
+    "$REF/BilateralFilter.cpp" "$HERE/ref_bilateral_shim.cpp"
 rm -rf "$OUT/build"
 echo "built $OUT/libref_cuda_O3.so and $OUT/libref_cuda_G.so"

@@ -47,6 +47,8 @@ _lib.oracle_normals.restype = None
 _lib.oracle_normals.argtypes = [_u32, _u32, _vp, _vp]
 _lib.oracle_mc_extract.restype = C.c_uint64
 _lib.oracle_mc_extract.argtypes = [_vp, _u32, _u32, _u32, _f, _f, _vp]
+_lib.oracle_bilateral.restype = None
+_lib.oracle_bilateral.argtypes = [_vp, _vp, C.c_int, C.c_int, C.c_int, _f, C.c_int, _f, C.c_int]
 _lib.oracle_hit_voxels.restype = None
 _lib.oracle_hit_voxels.argtypes = [_u32, _vp, _f, _f, _u32, _u32, _vp]
 
@@ -176,4 +178,42 @@ def mc_extract(dist, n, voxel, offset):
     if count:
         got = _lib.oracle_mc_extract(dist.ctypes.data, n[0], n[1], n[2], _fp(vox), _fp(off), out.ctypes.data)
         assert got == count
+    return out
+
+
+def bilateral_tables(sigma_colour, sigma_space, n_similarity=256):
+    """The look-up tables of BilateralFilter's constructor (reference src/BilateralFilter.cpp:15-42), float32 like the
+    reference (std::exp on a float argument is expf)."""
+    f = np.float32
+    radius = int(np.ceil(f(sigma_space) * f(1.5)))
+    size = 2 * radius + 1
+    inv_c = f(1.0) / (f(sigma_colour) * f(sigma_colour))
+    inv_s = f(1.0) / (f(sigma_space) * f(sigma_space))
+    kernel = np.empty(size * size, np.float32)
+    i = 0
+    for x in range(-radius, radius + 1):
+        for y in range(-radius, radius + 1):
+            kernel[i] = _expf(-(f(x * x + y * y)) * inv_s)
+            i += 1
+    similarity = np.array([_expf(-(f(d)) * inv_c) for d in range(n_similarity)], np.float32)
+    return kernel, similarity
+
+
+_libm = C.CDLL("libm.so.6")
+_libm.expf.restype = C.c_float
+_libm.expf.argtypes = [C.c_float]
+
+
+def _expf(x):
+    return np.float32(_libm.expf(C.c_float(float(x))))
+
+
+def bilateral(image, kernel, similarity):
+    """Filtered copy of a uint8 / uint16 (H, W) image with the given tables."""
+    image = np.ascontiguousarray(image)
+    bits = {np.dtype(np.uint8): 8, np.dtype(np.uint16): 16}[image.dtype]
+    out = np.empty_like(image)
+    size = int(round(np.sqrt(kernel.size)))
+    _lib.oracle_bilateral(image.ctypes.data, out.ctypes.data, bits, image.shape[1], image.shape[0], _fp(kernel), size,
+                          _fp(similarity), similarity.size)
     return out

@@ -23,6 +23,7 @@
 #include <stdint.h>
 #include <stddef.h>
 #include <string.h>
+#include <stdlib.h>
 #include <limits.h>
 #ifdef _OPENMP
 #include <omp.h>
@@ -505,4 +506,38 @@ uint64_t oracle_mc_extract(const float *dist, uint32_t nx, uint32_t ny, uint32_t
                 }
             }
     return n_out;
+}
+
+/* ---- bilateral filter -----------------------------------------------------------------------
+ * Restatement of BilateralFilter::filter_bpp (reference src/BilateralFilter.cpp:53-121) with the look-up tables of the
+ * constructor (:15-42) passed in: taps x-major then y (:81-82), kernel index advancing only for in-image taps (:105),
+ * `double w = k*s` from a float product, float sum/total updated through double (:100-103), floorf(sum/total) (:109).
+ * bits == 8 is the reference exactly (pinned against the compiled reference by tests/test_bilateral_cpu.py); bits == 16
+ * is undefined behaviour in the reference (256-entry table indexed up to 65535, one output byte per pixel): here the
+ * table has n_similarity entries (differences beyond it use the last one) and the output is 16-bit.              */
+void oracle_bilateral(const void *in, void *out, int bits, int width, int height, const float *kernel, int kernel_size,
+                      const float *similarity, int n_similarity) {
+    const int radius = (kernel_size - 1) / 2;
+#pragma omp parallel for schedule(static)
+    for (int y = 0; y < height; y++)
+        for (int x = 0; x < width; x++) {
+            const int centre = bits == 8 ? ((const uint8_t *)in)[(size_t)width * y + x] : ((const uint16_t *)in)[(size_t)width * y + x];
+            float total = 0, sum = 0;
+            int k = 0;
+            for (int cx = x - radius; cx <= x + radius; cx++)
+                for (int cy = y - radius; cy <= y + radius; cy++) {
+                    if (cx < 0 || cx >= width || cy < 0 || cy >= height) continue;
+                    const int v = bits == 8 ? ((const uint8_t *)in)[(size_t)width * cy + cx] : ((const uint16_t *)in)[(size_t)width * cy + cx];
+                    int delta = abs(v - centre);
+                    if (delta >= n_similarity) delta = n_similarity - 1;
+                    const float kw = kernel[k] * similarity[delta];
+                    const double w = kw;
+                    sum += (w * v);
+                    total += w;
+                    k++;
+                }
+            const int r = (int)floorf(sum / total);
+            if (bits == 8) ((uint8_t *)out)[(size_t)width * y + x] = (uint8_t)r;
+            else ((uint16_t *)out)[(size_t)width * y + x] = (uint16_t)r;
+        }
 }

@@ -19,6 +19,7 @@
 #include "../../tsdf_b200/include/RenderUtilities.hpp"
 #include "../../tsdf_b200/include/Definitions.hpp"
 #include "../../tsdf_b200/include/ply.hpp"
+#include "../../tsdf_b200/include/BilateralFilter.hpp"
 
 #include <algorithm>
 #include <cmath>
@@ -299,6 +300,21 @@ static void gpu_tests() {
     loaded.raycast(640, 480, *cam, v2, n2);
     CHECK(std::memcmp(v2.data(), vertices.data(), sizeof(float) * 3 * 640 * 480) == 0);
     CHECK(!loaded.load_from_file(path));                                    // a stub in the reference too
+
+    {   // bilateral filter class: in place, constants are fixed points, a depth edge survives
+        BilateralFilter filter(30.0f, 2.0f);
+        std::vector<uint16_t> flat(64 * 48, 1500), edge(64 * 48);
+        filter.filter(flat.data(), 64, 48);
+        bool same = true;
+        for (uint16_t v : flat) same = same && (v == 1500 || v == 1499);      // floorf(sum / total) in float may land one below
+        CHECK(same);
+        for (int i = 0; i < 64 * 48; i++) edge[i] = static_cast<uint16_t>(((i % 64) < 32 ? 1000 : 4000) + (i * 7) % 11);
+        filter.filter(edge.data(), 64, 48);
+        CHECK(edge[10 * 64 + 5] >= 999 && edge[10 * 64 + 5] <= 1010 && edge[10 * 64 + 60] >= 3999 && edge[10 * 64 + 60] <= 4010);
+        std::vector<uint8_t> grey(64 * 48, 77);
+        filter.filter(grey.data(), 64, 48);
+        CHECK(grey[100] == 77 || grey[100] == 76);
+    }
 
     volume.clear();
     volume.raycast(64, 48, *cam, vertices, normals);

@@ -43,6 +43,9 @@ SIGNATURES = {
     "tsdf_b200_raycast_resolve": (C.c_int, [_vp, _f, _f, C.c_float, _f, _f, _f, _u32, _u32, _vp, _vp, _vp, _vp]),
     "tsdf_b200_normals": (C.c_int, [_u32, _u32, _vp, _vp, _vp]),
     "tsdf_b200_selftest_division": (C.c_int, [C.c_float, _ull]),
+    "tsdf_b200_bilateral_u8": (C.c_int, [_vp, _vp, _u32, _u32, _vp, _u32, _vp, _u32, _vp]),
+    "tsdf_b200_bilateral_u16": (C.c_int, [_vp, _vp, _u32, _u32, _vp, _u32, _vp, _u32, _vp]),
+    "tsdf_b200_bilateral_host": (C.c_int, [_vp, C.c_int, _u32, _u32, _f, _u32, _f, _u32]),
     "tsdf_b200_mc_extract": (C.c_int, [_vp, _u32, _u32, _u32, _u32, _u32, _u32, _f, _f, C.POINTER(_vp), _ull, _vp]),
     "tsdf_b200_device_free": (None, [_vp]),
     "tsdf_b200_copy_to_host": (C.c_int, [_vp, _vp, C.c_size_t]),

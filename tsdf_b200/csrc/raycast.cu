@@ -161,12 +161,18 @@ raycast_kernel(const __grid_constant__ RayParams P) {
     for (int i = threadIdx.x; i < TSDF_B200_RAY_TABLE_LEN; i += blockDim.x) s_t[i] = P.table[i];
     __syncthreads();
 
-    // 128 threads = 4 warps, each an 8x4 pixel tile; block tile 16x8.
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const uint32_t imx = blockIdx.x * 16 + (warp & 1) * 8 + (lane & 7);
-    const uint32_t imy = blockIdx.y * 8 + (warp >> 1) * 4 + (lane >> 3);
+    // A warp marches one 8x4 pixel tile at a time.  The grid is sized to what is resident on the chip and every warp
+    // takes tiles w, w + W, w + 2W, ... (W = warps in the grid): rays differ by two orders of magnitude in cost and
+    // the cost is spatially correlated, so the interleaved assignment balances warps without a work counter, and the
+    // kernel has no tail of half-empty waves (one block per 16x8 tile ran 2.3 waves at 23% achieved occupancy).
+    const int lane = threadIdx.x & 31;
+    const uint32_t tiles_x = (P.width + 7) / 8, tiles_y = (P.height + 3) / 4, n_tiles = tiles_x * tiles_y;
+    const uint32_t warps_total = gridDim.x * (blockDim.x >> 5);
     uint32_t samples = 0;
 
+    for (uint32_t tile = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); tile < n_tiles; tile += warps_total) {
+    const uint32_t imx = (tile % tiles_x) * 8 + (lane & 7);
+    const uint32_t imy = (tile / tiles_x) * 4 + (lane >> 3);
     if (imx < P.width && imy < P.height) {
         const size_t pix = (size_t)imy * P.width + imx;
         const RaySetup R = ray_setup(P, imx, imy);
@@ -379,6 +385,8 @@ raycast_kernel(const __grid_constant__ RayParams P) {
             if (P.khit) P.khit[pix] = kh;
         }
     }
+    __syncwarp();
+    }
 
     if (P.n_samples) {
         for (int o = 16; o > 0; o >>= 1) samples += __shfl_down_sync(0xffffffffu, samples, o);
@@ -523,15 +531,23 @@ static int launch_march(RayParams &P, int fastdiv, cudaStream_t s) {
         P.occ_d = cd;
     }
     dim3 block(128);
-    dim3 grid((P.width + 15) / 16, (P.height + 7) / 8);
-    if (fastdiv) {
-        if (P.occ) raycast_kernel<true, true, SLAB><<<grid, block, 0, s>>>(P);
-        else       raycast_kernel<true, false, SLAB><<<grid, block, 0, s>>>(P);
-    } else {
-        if (P.occ) raycast_kernel<false, true, SLAB><<<grid, block, 0, s>>>(P);
-        else       raycast_kernel<false, false, SLAB><<<grid, block, 0, s>>>(P);
-    }
-    return (int)cudaGetLastError();
+    const uint32_t n_tiles = ((P.width + 7) / 8) * ((P.height + 3) / 4);
+    auto launch = [&](auto kernel) -> int {
+        // resident blocks on this device (queried once per kernel variant)
+        static int resident = 0;
+        if (resident == 0) {
+            int dev = 0, sms = 0, per_sm = 0;
+            TSDF_CUDA_TRY(cudaGetDevice(&dev));
+            TSDF_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+            TSDF_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, 128, 0));
+            resident = sms * (per_sm > 0 ? per_sm : 1);
+        }
+        const uint32_t blocks = (n_tiles + 3) / 4 < (uint32_t)resident ? (n_tiles + 3) / 4 : (uint32_t)resident;
+        kernel<<<blocks, block, 0, s>>>(P);
+        return (int)cudaGetLastError();
+    };
+    if (fastdiv) return P.occ ? launch(raycast_kernel<true, true, SLAB>) : launch(raycast_kernel<true, false, SLAB>);
+    return P.occ ? launch(raycast_kernel<false, true, SLAB>) : launch(raycast_kernel<false, false, SLAB>);
 }
 
 extern "C" int tsdf_b200_raycast_ex(const float *d_dist, uint32_t nx, uint32_t ny, uint32_t nz,

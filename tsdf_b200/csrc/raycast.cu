@@ -13,6 +13,7 @@
 // Every sample that IS evaluated uses the reference's exact operation order.
 #include "common.cuh"
 #include <math_constants.h>
+#include <stdlib.h>
 
 namespace tsdf {
 
@@ -36,6 +37,8 @@ struct RayParams {
     int32_t *khit;
     long long *keys;
     unsigned long long *n_samples;
+    unsigned int *tile_counter;  // work counter for dynamic tile scheduling (zeroed before the launch) or nullptr
+    int debug_iters;             // TSDF_B200_DEBUG_ITERS: khit receives loop iterations per ray (tuning aid)
 };
 
 template <bool FASTDIV>
@@ -161,23 +164,30 @@ raycast_kernel(const __grid_constant__ RayParams P) {
     for (int i = threadIdx.x; i < TSDF_B200_RAY_TABLE_LEN; i += blockDim.x) s_t[i] = P.table[i];
     __syncthreads();
 
-    // A warp marches one 8x4 pixel tile at a time.  The grid is sized to what is resident on the chip and every warp
-    // takes tiles w, w + W, w + 2W, ... (W = warps in the grid): rays differ by two orders of magnitude in cost and
-    // the cost is spatially correlated, so the interleaved assignment balances warps without a work counter, and the
-    // kernel has no tail of half-empty waves (one block per 16x8 tile ran 2.3 waves at 23% achieved occupancy).
+    // A warp marches one 8x4 pixel tile at a time.  The grid is sized to what is resident on the chip and warps draw
+    // tiles from a work counter: a tile costs between ~10 and ~400 loop iterations (tools/ray_iters.py), so with one
+    // block per 16x8 tile the kernel ran 2.3 waves at 23% achieved occupancy, and with a static interleaved assignment
+    // the slowest warp still took twice the mean.  Without a counter (no occupancy buffer to keep it in) warps take
+    // tiles w, w + W, w + 2W, ...
     const int lane = threadIdx.x & 31;
     const uint32_t tiles_x = (P.width + 7) / 8, tiles_y = (P.height + 3) / 4, n_tiles = tiles_x * tiles_y;
     const uint32_t warps_total = gridDim.x * (blockDim.x >> 5);
     uint32_t samples = 0;
+    auto next_tile = [&](uint32_t previous, bool first) -> uint32_t {
+        if (!P.tile_counter) return first ? blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5) : previous + warps_total;
+        uint32_t t = 0;
+        if (lane == 0) t = atomicAdd(P.tile_counter, 1u);
+        return __shfl_sync(0xffffffffu, t, 0);
+    };
 
-    for (uint32_t tile = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); tile < n_tiles; tile += warps_total) {
+    for (uint32_t tile = next_tile(0, true); tile < n_tiles; tile = next_tile(tile, false)) {
     const uint32_t imx = (tile % tiles_x) * 8 + (lane & 7);
     const uint32_t imy = (tile / tiles_x) * 4 + (lane >> 3);
     if (imx < P.width && imy < P.height) {
         const size_t pix = (size_t)imy * P.width + imx;
         const RaySetup R = ray_setup(P, imx, imy);
         float ip[3] = { CUDART_NAN_F, CUDART_NAN_F, CUDART_NAN_F };
-        int kh = -1;
+        int kh = -1, dbg_iters = 0;
         float s_hit = 0.0f;
 
         if (R.intersects) {
@@ -205,6 +215,7 @@ raycast_kernel(const __grid_constant__ RayParams P) {
             int clx = -1, cly = -1, clz = -1;     // corner cache key
             float c000 = 0, c001 = 0, c010 = 0, c011 = 0, c100 = 0, c101 = 0, c110 = 0, c111 = 0;
             bool cpos = false;                    // all 8 cached corners inside the positive band
+            float lip_inv = 0.0f, lip_margin = 3.0e38f;   // level 3: 1 / (Lipschitz bound per step), absolute slack
 
             int k = 0, k_stop = TSDF_B200_MAX_SAMPLES - 1;     // samples k = 0..4401 exist (:369)
             if (SLAB) {
@@ -230,7 +241,9 @@ raycast_kernel(const __grid_constant__ RayParams P) {
                 }
             }
 
+            int iters = 0;
             while (true) {
+                iters++;
                 if (k > k_stop) break;
                 const float t = s_t[k];
                 if (k > 0 && t >= max_t) break;                         // sample k>0 exists only if t_k < max_t (:360-365)
@@ -295,6 +308,8 @@ raycast_kernel(const __grid_constant__ RayParams P) {
                 }
 
                 float s;
+                bool uvw_in_cell = false;
+                float cell_lo[3] = { 0.0f, 0.0f, 0.0f };
                 if (oob) {
                     s = CUDART_NAN_F;                                                          // :77-80
                     samples++;
@@ -333,15 +348,31 @@ raycast_kernel(const __grid_constant__ RayParams P) {
                             const bool finite = (c000 == c000) && (c001 == c001) && (c010 == c010) && (c011 == c011) &&
                                                 (c100 == c100) && (c101 == c101) && (c110 == c110) && (c111 == c111);
                             cpos = finite && cmin >= P.occ_lo && cmax <= P.occ_hi;
+                            // level 3 (below): the interpolant is multilinear, so with weights in [0,1] its derivative
+                            // along u is a convex combination of the four corner differences along x, and likewise for
+                            // v and w: |ds/dt| <= sum_a G_a * |dir_a| / voxel_a with G_a the largest corner difference
+                            const float gx = fmaxf(fmaxf(fabsf(c100 - c000), fabsf(c101 - c001)), fmaxf(fabsf(c110 - c010), fabsf(c111 - c011)));
+                            const float gy = fmaxf(fmaxf(fabsf(c010 - c000), fabsf(c011 - c001)), fmaxf(fabsf(c110 - c100), fabsf(c111 - c101)));
+                            const float gz = fmaxf(fmaxf(fabsf(c001 - c000), fabsf(c011 - c010)), fmaxf(fabsf(c101 - c100), fabsf(c111 - c110)));
+                            const float lt = (gx * fabsf(dir[0]) * P.rvs[0] + gy * fabsf(dir[1]) * P.rvs[1] + gz * fabsf(dir[2]) * P.rvs[2]) * step;
+                            // per-step bound inflated by 1% (rounding of the bound itself)
+                            lip_inv = (finite && lt < 3.0e37f) ? 0.99f / fmaxf(lt, 1.0e-30f) : 0.0f;
+                            // an evaluated sample differs from the ideal interpolant at the ideal position by the rounding of
+                            // p (a few ulps of a coordinate as large as the volume: < 1e-6 * n voxels, four times the estimate)
+                            // times the gradient bound, plus ~10 roundings of terms no larger than the largest corner
+                            lip_margin = (gx + gy + gz) * (1.0e-6f * (float)(max(max(P.nx, P.ny), P.nz) + 2u)) +
+                                         1.0e-5f * fmaxf(fabsf(cmin), fabsf(cmax));
                         }
                     }
                     const float u = uvw[0], v = uvw[1], w = uvw[2];
+                    uvw_in_cell = u >= 0.0f && u <= 1.0f && v >= 0.0f && v <= 1.0f && w >= 0.0f && w <= 1.0f;
+                    cell_lo[0] = lcs[0]; cell_lo[1] = lcs[1]; cell_lo[2] = lcs[2];
 
                     // ---- level 2: a cell whose 8 corners are all in the positive band ----------------------------
                     // With weights in [0,1] every product is >= 0 and one is >= corner/8 > 0, so the sample is > 0
                     // without evaluating it; the same holds for every following sample that stays inside the cell
                     // (pulled in by the guard band, so that `lower` and the weights' range cannot flip).
-                    if (SKIP && cpos && u >= 0.0f && u <= 1.0f && v >= 0.0f && v <= 1.0f && w >= 0.0f && w <= 1.0f) {
+                    if (SKIP && cpos && uvw_in_cell) {
                         float t_gain = 3.0e30f;
 #pragma unroll
                         for (int a = 0; a < 3; a++) {
@@ -372,8 +403,28 @@ raycast_kernel(const __grid_constant__ RayParams P) {
                     if (!SLAB) hit_vertex(P, R, t, s, ip);
                     break;
                 }
+                // ---- level 3: samples that cannot have reached zero yet -----------------------------------------------
+                // While the ray stays in this cell (guard band as in level 2, so `lower` and the weights' range cannot
+                // flip) sample k+j is at least s - j * (Lipschitz bound per step) - rounding slack: the first j for which
+                // that is still positive need no evaluation.  This is what bounds the cost of a ray that skims a surface
+                // at a small positive distance for thousands of samples (one such ray used to set the kernel's run time).
+                if (SKIP && !oob && lip_inv > 0.0f) {
+                    const int j = (int)fminf((s - lip_margin) * lip_inv, 5000.0f);       // NaN / negative -> 0 or less
+                    if (j >= 1 && uvw_in_cell) {
+                        float t_gain = 3.0e30f;
+#pragma unroll
+                        for (int a = 0; a < 3; a++) {
+                            const float g = 0.02f * P.vs[a];
+                            const float dlo = p[a] - (cell_lo[a] + g), dhi = (cell_lo[a] + P.vs[a] - g) - p[a];
+                            const float ta = sgn[a] > 0 ? dhi * ainv[a] : (sgn[a] < 0 ? dlo * ainv[a] : ((dlo >= 0.0f && dhi >= 0.0f) ? 3.0e30f : -1.0f));
+                            t_gain = fminf(t_gain, (dlo >= 0.0f && dhi >= 0.0f) ? ta : -1.0f);
+                        }
+                        k += min(j, safe_steps(s_t, k, t, t_gain, inv_step));
+                    }
+                }
                 k++;
             }
+            dbg_iters = iters;
         }
         if (SLAB) {
             // key: first hit along the ray wins an all-reduce(min); the sample value rides in the low word
@@ -382,7 +433,7 @@ raycast_kernel(const __grid_constant__ RayParams P) {
             P.vertices[3 * pix + 0] = ip[0];
             P.vertices[3 * pix + 1] = ip[1];
             P.vertices[3 * pix + 2] = ip[2];
-            if (P.khit) P.khit[pix] = kh;
+            if (P.khit) P.khit[pix] = P.debug_iters ? dbg_iters : kh;
         }
     }
     __syncwarp();
@@ -513,7 +564,9 @@ static int fill_params(RayParams &P, const float *d_dist, uint32_t nx, uint32_t 
     P.occ = nullptr; P.occ_d = nullptr; P.nbx = P.nby = P.nbz = 0;
     P.occ_lo = trunc * kOccLoFrac; P.occ_hi = trunc * kOccHiFrac;
     P.z_base = 0; P.z_lo = 0; P.z_hi = nz;
-    P.vertices = nullptr; P.khit = nullptr; P.keys = nullptr; P.n_samples = nullptr;
+    P.vertices = nullptr; P.khit = nullptr; P.keys = nullptr; P.n_samples = nullptr; P.tile_counter = nullptr;
+    static const int dbg = getenv("TSDF_B200_DEBUG_ITERS") ? atoi(getenv("TSDF_B200_DEBUG_ITERS")) : 0;
+    P.debug_iters = dbg;
     return 0;
 }
 
@@ -529,6 +582,12 @@ static int launch_march(RayParams &P, int fastdiv, cudaStream_t s) {
         distance_pass_kernel<1, false><<<g, 256, 0, s>>>(cd, tmp, (int)P.nbx, (int)P.nby, (int)P.nbz);
         distance_pass_kernel<2, false><<<g, 256, 0, s>>>(tmp, cd, (int)P.nbx, (int)P.nby, (int)P.nbz);
         P.occ_d = cd;
+        // the scratch third of the buffer is free again: its first aligned word becomes the tile counter
+        uint8_t *word = (uint8_t *)(((uintptr_t)tmp + 3) & ~(uintptr_t)3);
+        if (word + 4 <= tmp + nb) {
+            P.tile_counter = reinterpret_cast<unsigned int *>(word);
+            TSDF_CUDA_TRY(cudaMemsetAsync(P.tile_counter, 0, 4, s));
+        }
     }
     dim3 block(128);
     const uint32_t n_tiles = ((P.width + 7) / 8) * ((P.height + 3) / 4);

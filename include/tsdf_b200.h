@@ -142,6 +142,21 @@ int tsdf_b200_raycast_slab(const float *d_dist_slab, uint32_t nx, uint32_t ny, u
                            const uint8_t *d_occ_slab, long long *d_keys,
                            unsigned long long *d_n_samples, int fastdiv, void *stream);
 
+/* Z-sharded raycast, march phase, INTERLEAVED slabs: the volume's planes are cut into global slabs of slab_planes planes
+ * (a multiple of 8) dealt to `world` ranks round robin (slab s belongs to rank s % world) — surfaces then spread over the
+ * ranks instead of landing in one contiguous slab, and the march balances.  d_dist_local holds this rank's slabs back to
+ * back in ascending order, each followed by ONE halo plane (slab_planes + 1 planes per slab; the halo of a slab that ends
+ * the volume is unused).  d_occ_global is an occupancy grid of the WHOLE volume (tsdf_b200_occupancy_bytes(nx,ny,nz)) in
+ * which only this rank's bricks were ever flagged: integrate each slab with d_occ = grid + brick offset of the slab.
+ * Keys as in tsdf_b200_raycast_slab: min-reduce over ranks, then tsdf_b200_raycast_resolve.                      */
+int tsdf_b200_raycast_interleaved(const float *d_dist_local, uint32_t nx, uint32_t ny, uint32_t nz,
+                                  uint32_t slab_planes, uint32_t world, uint32_t rank,
+                                  const float voxel[3], const float space_min[3], const float space_max[3],
+                                  float trunc, const float origin[3], const float rot[9], const float kinv[9],
+                                  uint32_t width, uint32_t height, const float *d_table,
+                                  const uint8_t *d_occ_global, long long *d_keys,
+                                  unsigned long long *d_n_samples, int fastdiv, void *stream);
+
 /* Z-sharded raycast, resolve phase: reduced keys -> vertices (NaN^3 for INT64_MAX) and optional k_hit,
  * with the hit formula of RayCaster/GPURaycaster.cu:336-348.                                        */
 int tsdf_b200_raycast_resolve(const long long *d_keys, const float space_min[3], const float space_max[3],

@@ -519,3 +519,45 @@ def test_volume_offset_and_clear_semantics(G):
         assert_bits_equal(V, ov.raycast(320, 240, cam.pose, cam.kinv)[0], f"vertices step {step}")
         vol.clear(); ov.clear()
     vol.close()
+
+
+@pytest.mark.parametrize("world,slab", [(2, 16), (3, 8), (8, 16)])
+def test_interleaved_slabs_equal_whole(G, world, slab):
+    """Interleaved Z-slabs (the multi-GPU layout of ShardedEngine): every emulated rank integrates its own slabs (+ halo
+    planes) into its own arrays and its own whole-volume occupancy grid, marches all rays over the cells it owns; the
+    min over the ranks' keys, resolved, must equal the single-volume raycast bit for bit, and the ranks' planes must equal
+    the single volume's planes."""
+    import torch
+    from tsdf_b200 import scenes, sharded
+    n, phys = (96, 80, 112), (3000.0, 2500.0, 3000.0)
+    whole = sharded.ShardedEngine(n, phys)
+    ranks = [sharded.ShardedEngine(n, phys, rank=r, world=world, layout="interleaved", slab=slab) for r in range(world)]
+    cams = [scenes.orbit_camera(i, 12) for i in (0, 2, 5)]
+    counts = []
+    for cam in cams:
+        k = cam.k.copy(); k[:2] *= 0.5
+        cam.k = k
+        cam.kinv = np.linalg.inv(k.astype(np.float64)).astype(np.float32)
+        depth = torch.from_numpy(scenes.render_depth(cam, 320, 240)).cuda()
+        total = whole.integrate(depth, cam, count=True)
+        assert sum(e.integrate(depth, cam, count=True) for e in ranks) == total
+        counts.append(total)
+    assert sum(counts) > 0
+    wd = whole.dist.view(n[2], -1)
+    for e in ranks:
+        ld = e.dist.view(-1, n[0] * n[1])
+        for j, (z0, z1) in enumerate(e.slabs):
+            stored = (z1 - z0) + (1 if z1 < n[2] else 0)
+            assert torch.equal(ld[j * (slab + 1): j * (slab + 1) + stored].view(torch.int32), wd[z0:z0 + stored].view(torch.int32))
+    cam = cams[1]
+    whole.raycast(320, 240, cam)
+    keys = None
+    for e in ranks:
+        k = e.march(320, 240, cam).clone()
+        keys = k if keys is None else torch.minimum(keys, k)
+    ranks[0].keys.copy_(keys)
+    ranks[0].resolve(320, 240, cam)
+    torch.cuda.synchronize()
+    assert_bits_equal(ranks[0].vertices.cpu().numpy(), whole.vertices.cpu().numpy(), "vertices")
+    assert_bits_equal(ranks[0].normals.cpu().numpy(), whole.normals.cpu().numpy(), "normals")
+    assert int((~torch.isnan(whole.vertices.view(-1, 3)[:, 0])).sum()) > 5000

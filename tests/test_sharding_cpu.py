@@ -73,3 +73,14 @@ def test_two_rank_gloo_sharded_raycast(tmp_path):
     outs = [p.communicate(timeout=300)[0] for p in procs]
     assert all(p.returncode == 0 for p in procs), "\n".join(outs)
     assert "SHARDED_OK" in outs[0]
+
+
+def test_interleaved_slabs_partition_the_volume():
+    from tsdf_b200.sharded import interleaved_slabs
+    for nz, world, slab in [(512, 8, 16), (112, 3, 8), (100, 4, 16), (16, 8, 16)]:
+        seen = []
+        for r in range(world):
+            own = interleaved_slabs(nz, world, r, slab)
+            assert all((z0 // slab) % world == r and z0 % slab == 0 and z1 - z0 <= slab for z0, z1 in own)
+            seen += [z for z0, z1 in own for z in range(z0, z1)]
+        assert sorted(seen) == list(range(nz))

@@ -33,6 +33,10 @@ struct RayParams {
     uint32_t nbx, nby, nbz;      // occupancy grid dimensions (local planes when sharded)
     float occ_lo, occ_hi;        // positive band
     uint32_t z_base, z_lo, z_hi; // Z-slab: global z of array plane 0; cells owned by this rank start in [z_lo, z_hi)
+    // Interleaved slabs (cyc_g > 0, SLAB kernels): global slabs of cyc_s planes are dealt to cyc_g ranks round robin, this
+    // rank (cyc_r) stores its slabs back to back, each followed by one halo plane (cyc_s + 1 planes per slab); the occupancy
+    // grid covers the WHOLE volume and only bricks of owned slabs (and the halo's) are ever flagged in it
+    uint32_t cyc_s, cyc_g, cyc_r;
     float *vertices;
     int32_t *khit;
     long long *keys;
@@ -218,7 +222,7 @@ raycast_kernel(const __grid_constant__ RayParams P) {
             float lip_inv = 0.0f, lip_margin = 3.0e38f;   // level 3: 1 / (Lipschitz bound per step), absolute slack
 
             int k = 0, k_stop = TSDF_B200_MAX_SAMPLES - 1;     // samples k = 0..4401 exist (:369)
-            if (SLAB) {
+            if (SLAB && P.cyc_g == 0) {
                 // Parameter interval in which a sample's cell can start inside [z_lo, z_hi), with a voxel of slack.
                 const float zl = (P.z_lo == 0) ? -3.0e38f : ((float)P.z_lo - 1.0f) * P.vs[2];
                 const float zh = (P.z_hi >= P.nz) ? 3.0e38f : ((float)P.z_hi + 1.5f) * P.vs[2];
@@ -278,7 +282,7 @@ raycast_kernel(const __grid_constant__ RayParams P) {
                 // point and every skipped sample keep 1.05 voxels away from the low faces of the volume.
                 if (SKIP && !oob) {
                     const int b[3] = { vox[0] / TSDF_B200_BRICK, vox[1] / TSDF_B200_BRICK, vox[2] / TSDF_B200_BRICK };
-                    const int bz_local = b[2] - (SLAB ? (int)(P.z_base / TSDF_B200_BRICK) : 0);
+                    const int bz_local = b[2] - ((SLAB && P.cyc_g == 0) ? (int)(P.z_base / TSDF_B200_BRICK) : 0);
                     const bool in_grid = !SLAB || (bz_local >= 0 && bz_local < (int)P.nbz);
                     const int cd = in_grid ? (int)__ldg(P.occ_d + ((size_t)bz_local * P.nby + b[1]) * P.nbx + b[0]) : 0;
                     if (cd >= 1) {
@@ -326,14 +330,46 @@ raycast_kernel(const __grid_constant__ RayParams P) {
                         low[a] = l;
                         lcs[a] = lc;
                     }
-                    if (SLAB && ((uint32_t)low[2] < P.z_lo || (uint32_t)low[2] >= P.z_hi)) { k++; continue; }   // another rank's sample
+                    if (SLAB) {
+                        bool mine;
+                        if (P.cyc_g > 0) mine = ((uint32_t)low[2] / P.cyc_s) % P.cyc_g == P.cyc_r;
+                        else             mine = (uint32_t)low[2] >= P.z_lo && (uint32_t)low[2] < P.z_hi;
+                        if (!mine) {
+                            // another rank's cell: nothing of it is evaluated here.  Leave it the way level 2 leaves a cell
+                            // that is certainly positive (guard band, so that `lower` cannot flip) instead of one sample
+                            // at a time — with interleaved slabs a ray meets such cells at every slab boundary.
+                            float t_gain = -1.0f;
+                            if (SKIP && uvw[0] >= 0.0f && uvw[0] <= 1.0f && uvw[1] >= 0.0f && uvw[1] <= 1.0f && uvw[2] >= 0.0f && uvw[2] <= 1.0f) {
+                                t_gain = 3.0e30f;
+#pragma unroll
+                                for (int a = 0; a < 3; a++) {
+                                    const float g = 0.02f * P.vs[a];
+                                    const float dlo = p[a] - (lcs[a] + g), dhi = (lcs[a] + P.vs[a] - g) - p[a];
+                                    const float ta = sgn[a] > 0 ? dhi * ainv[a] : (sgn[a] < 0 ? dlo * ainv[a] : ((dlo >= 0.0f && dhi >= 0.0f) ? 3.0e30f : -1.0f));
+                                    t_gain = fminf(t_gain, (dlo >= 0.0f && dhi >= 0.0f) ? ta : -1.0f);
+                                }
+                            }
+                            k += 1 + (SKIP ? safe_steps(s_t, k, t, t_gain, inv_step) : 0);
+                            continue;
+                        }
+                    }
                     if (low[0] != clx || low[1] != cly || low[2] != clz) {
                         clx = low[0]; cly = low[1]; clz = low[2];
                         // tsdf_value_at (TSDF_utilities.cu:29-37): upper clamp, 32-bit index arithmetic
-                        const uint32_t zb = SLAB ? P.z_base : 0u;
                         const uint32_t x0 = min((uint32_t)clx, P.nx - 1), x1 = min((uint32_t)clx + 1, P.nx - 1);
                         const uint32_t y0 = P.nx * min((uint32_t)cly, P.ny - 1), y1 = P.nx * min((uint32_t)cly + 1, P.ny - 1);
-                        const uint32_t z0 = P.nx * P.ny * (min((uint32_t)clz, P.nz - 1) - zb), z1 = P.nx * P.ny * (min((uint32_t)clz + 1, P.nz - 1) - zb);
+                        // array plane of global plane z: whole volume, contiguous slab, or interleaved slabs (+1 halo each)
+                        const uint32_t zg0 = min((uint32_t)clz, P.nz - 1), zg1 = min((uint32_t)clz + 1, P.nz - 1);
+                        uint32_t zl0, zl1;
+                        if (SLAB && P.cyc_g > 0) {
+                            const uint32_t sg = zg0 / P.cyc_s;
+                            zl0 = (sg / P.cyc_g) * (P.cyc_s + 1u) + (zg0 - sg * P.cyc_s);
+                            zl1 = zl0 + (zg1 - zg0);                      // the halo plane follows the slab's last plane
+                        } else {
+                            const uint32_t zb = SLAB ? P.z_base : 0u;
+                            zl0 = zg0 - zb; zl1 = zg1 - zb;
+                        }
+                        const uint32_t z0 = P.nx * P.ny * zl0, z1 = P.nx * P.ny * zl1;
                         c000 = __ldg(P.dist + (size_t)(z0 + y0 + x0));
                         c001 = __ldg(P.dist + (size_t)(z1 + y0 + x0));
                         c010 = __ldg(P.dist + (size_t)(z0 + y1 + x0));
@@ -564,6 +600,7 @@ static int fill_params(RayParams &P, const float *d_dist, uint32_t nx, uint32_t 
     P.occ = nullptr; P.occ_d = nullptr; P.nbx = P.nby = P.nbz = 0;
     P.occ_lo = trunc * kOccLoFrac; P.occ_hi = trunc * kOccHiFrac;
     P.z_base = 0; P.z_lo = 0; P.z_hi = nz;
+    P.cyc_s = 0; P.cyc_g = 0; P.cyc_r = 0;
     P.vertices = nullptr; P.khit = nullptr; P.keys = nullptr; P.n_samples = nullptr; P.tile_counter = nullptr;
     static const int dbg = getenv("TSDF_B200_DEBUG_ITERS") ? atoi(getenv("TSDF_B200_DEBUG_ITERS")) : 0;
     P.debug_iters = dbg;
@@ -656,6 +693,26 @@ extern "C" int tsdf_b200_raycast_slab(const float *d_dist_slab, uint32_t nx, uin
     const BrickDims nb = brick_dims(nx, ny, z_planes);
     P.nbx = nb.bx; P.nby = nb.by; P.nbz = nb.bz;
     P.z_base = z_base; P.z_lo = z_lo; P.z_hi = z_hi;
+    P.keys = d_keys; P.n_samples = d_n_samples;
+    return launch_march<true>(P, fastdiv, (cudaStream_t)stream);
+}
+
+extern "C" int tsdf_b200_raycast_interleaved(const float *d_dist_local, uint32_t nx, uint32_t ny, uint32_t nz,
+                                             uint32_t slab_planes, uint32_t world, uint32_t rank,
+                                             const float voxel[3], const float space_min[3], const float space_max[3],
+                                             float trunc, const float origin[3], const float rot[9], const float kinv[9],
+                                             uint32_t width, uint32_t height, const float *d_table,
+                                             const uint8_t *d_occ_global, long long *d_keys,
+                                             unsigned long long *d_n_samples, int fastdiv, void *stream) {
+    if (!d_dist_local || !d_keys || world == 0 || rank >= world) return TSDF_B200_EINVAL;
+    if (slab_planes == 0 || slab_planes % TSDF_B200_BRICK != 0) return TSDF_B200_EINVAL;
+    RayParams P;
+    int rc = fill_params(P, d_dist_local, nx, ny, nz, voxel, space_min, space_max, trunc, origin, rot, kinv, width, height, d_table, &fastdiv);
+    if (rc) return rc;
+    P.occ = d_occ_global;
+    const BrickDims nb = brick_dims(nx, ny, nz);
+    P.nbx = nb.bx; P.nby = nb.by; P.nbz = nb.bz;
+    P.cyc_s = slab_planes; P.cyc_g = world; P.cyc_r = rank;
     P.keys = d_keys; P.n_samples = d_n_samples;
     return launch_march<true>(P, fastdiv, (cudaStream_t)stream);
 }

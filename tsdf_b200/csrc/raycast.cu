@@ -387,6 +387,9 @@ raycast_kernel(const __grid_constant__ RayParams P) {
                             // level 3 (below): the interpolant is multilinear, so with weights in [0,1] its derivative
                             // along u is a convex combination of the four corner differences along x, and likewise for
                             // v and w: |ds/dt| <= sum_a G_a * |dir_a| / voxel_a with G_a the largest corner difference
+                            // (not needed for a cell that level 2 skips as a whole)
+                            lip_inv = 0.0f;
+                            if (!cpos) {
                             const float gx = fmaxf(fmaxf(fabsf(c100 - c000), fabsf(c101 - c001)), fmaxf(fabsf(c110 - c010), fabsf(c111 - c011)));
                             const float gy = fmaxf(fmaxf(fabsf(c010 - c000), fabsf(c011 - c001)), fmaxf(fabsf(c110 - c100), fabsf(c111 - c101)));
                             const float gz = fmaxf(fmaxf(fabsf(c001 - c000), fabsf(c011 - c010)), fmaxf(fabsf(c101 - c100), fabsf(c111 - c110)));
@@ -398,6 +401,7 @@ raycast_kernel(const __grid_constant__ RayParams P) {
                             // times the gradient bound, plus ~10 roundings of terms no larger than the largest corner
                             lip_margin = (gx + gy + gz) * (1.0e-6f * (float)(max(max(P.nx, P.ny), P.nz) + 2u)) +
                                          1.0e-5f * fmaxf(fabsf(cmin), fabsf(cmax));
+                            }
                         }
                     }
                     const float u = uvw[0], v = uvw[1], w = uvw[2];

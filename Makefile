@@ -6,7 +6,7 @@ NVCC      ?= /usr/local/cuda/bin/nvcc
 ARCH      := -gencode arch=compute_100a,code=sm_100a
 NVCCFLAGS := $(ARCH) -O3 -std=c++17 -lineinfo -fmad=false -Xcompiler -fPIC,-Wall,-Wno-unused-function
 CSRC      := tsdf_b200/csrc
-OBJS      := $(CSRC)/integrate.o $(CSRC)/raycast.o $(CSRC)/misc.o $(CSRC)/volume.o $(CSRC)/mc.o $(CSRC)/bilateral.o
+OBJS      := $(CSRC)/integrate.o $(CSRC)/raycast.o $(CSRC)/misc.o $(CSRC)/volume.o $(CSRC)/mc.o $(CSRC)/bilateral.o $(CSRC)/exchange.o
 
 all: lib oracle classes
 
@@ -14,6 +14,12 @@ lib: tsdf_b200/libtsdf_b200.so
 
 $(CSRC)/%.o: $(CSRC)/%.cu $(CSRC)/common.cuh $(CSRC)/integrate_rigid.cuh $(CSRC)/mc_tables.h include/tsdf_b200.h
 	$(NVCC) $(NVCCFLAGS) -c $< -o $@
+
+# instrumented build of the raycast for tools/ray_iters.py (per-ray iteration classes, per-tile clocks); not the product
+dbg: tsdf_b200/libtsdf_b200_dbg.so
+tsdf_b200/libtsdf_b200_dbg.so: $(OBJS)
+	$(NVCC) $(NVCCFLAGS) -DTSDF_RAY_DEBUG -c $(CSRC)/raycast.cu -o $(CSRC)/raycast_dbg.o
+	$(NVCC) $(ARCH) -shared -o $@ $(subst raycast.o,raycast_dbg.o,$(OBJS))
 
 tsdf_b200/libtsdf_b200.so: $(OBJS)
 	$(NVCC) $(ARCH) -shared -o $@ $(OBJS)

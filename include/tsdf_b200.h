@@ -39,6 +39,10 @@ extern "C" {
 #define TSDF_B200_RAY_TABLE_LEN 4416
 /* Edge of an occupancy brick in voxels (empty-space skipping grid). */
 #define TSDF_B200_BRICK 8
+/* Most GPUs one exchange call can address (tsdf_b200_bricks_push, tsdf_b200_raycast_tiles). */
+#define TSDF_B200_MAX_PEERS 16
+/* Bytes of an exported peer-memory handle (tsdf_b200_peer_alloc / tsdf_b200_peer_open). */
+#define TSDF_B200_PEER_HANDLE_BYTES 64
 
 const char *tsdf_b200_version(void);
 /* Text for any return code of this library (cudaGetErrorString for positive codes). */
@@ -156,6 +160,43 @@ int tsdf_b200_raycast_interleaved(const float *d_dist_local, uint32_t nx, uint32
                                   uint32_t width, uint32_t height, const float *d_table,
                                   const uint8_t *d_occ_global, long long *d_keys,
                                   unsigned long long *d_n_samples, int fastdiv, void *stream);
+
+/* ---- Multi-GPU, image-sharded raycast over peer memory (no counterpart in the single-GPU reference; the per-sample
+ * arithmetic is RayCaster/GPURaycaster.cu:265-377 as in tsdf_b200_raycast) ------------------------------------------------
+ *
+ * Every GPU holds, next to its own slabs, a full-size copy of the distance volume (a "replica") in which only surface bricks
+ * are ever valid.  Per frame: integrate the owned slabs (interleaved layout of tsdf_b200_raycast_interleaved, occupancy
+ * grid of the whole volume), max-reduce the brick flags over the ranks, tsdf_b200_bricks_push, barrier,
+ * tsdf_b200_raycast_tiles, barrier, tsdf_b200_normals.
+ *
+ * tsdf_b200_bricks_push: copies every owned brick that has a flagged brick in its 27-neighbourhood (d_occ_global, merged
+ * flags) from this rank's slabs into the n_dst replicas d_dst[0..n_dst) (host array of device pointers; peers' replicas
+ * are written through NVLink).  That set covers every voxel a ray can read: a sample is evaluated only inside a flagged
+ * brick b and reads voxels of [8b-1, 8b+8]^3.  d_n_bricks (optional) += bricks copied.                                  */
+int tsdf_b200_bricks_push(const float *d_dist_local, uint32_t nx, uint32_t ny, uint32_t nz,
+                          uint32_t slab_planes, uint32_t world, uint32_t rank,
+                          const uint8_t *d_occ_global, uint32_t n_dst, float *const *d_dst,
+                          unsigned long long *d_n_bricks, void *stream);
+
+/* tsdf_b200_raycast_ex restricted to this rank's pixel tiles: of every `world` consecutive 8x4-pixel tiles rank `rank`
+ * marches one (rotating from tile row to tile row), against d_dist = its replica and d_occ = the merged occupancy grid, and
+ * stores each vertex into all n_out vertex maps d_vertices_out[0..n_out) (host array of device pointers, 3*width*height
+ * floats each).  After every rank's call (and a barrier) each map holds the complete single-GPU result.             */
+int tsdf_b200_raycast_tiles(const float *d_dist, uint32_t nx, uint32_t ny, uint32_t nz,
+                            const float voxel[3], const float space_min[3], const float space_max[3],
+                            float trunc, const float origin[3], const float rot[9], const float kinv[9],
+                            uint32_t width, uint32_t height, const float *d_table,
+                            const uint8_t *d_occ, uint32_t world, uint32_t rank,
+                            uint32_t n_out, float *const *d_vertices_out,
+                            unsigned long long *d_n_samples, int fastdiv, void *stream);
+
+/* Peer memory for the two calls above: a cudaMalloc block plus its CUDA IPC handle (64 bytes, to be sent to the other
+ * processes of the box); tsdf_b200_peer_open maps another process's block (peer access enabled on demand).          */
+int tsdf_b200_peer_alloc(size_t bytes, void **d_ptr, unsigned char handle[TSDF_B200_PEER_HANDLE_BYTES]);
+int tsdf_b200_peer_open(const unsigned char handle[TSDF_B200_PEER_HANDLE_BYTES], void **d_ptr);
+int tsdf_b200_peer_close(void *d_ptr);
+int tsdf_b200_peer_free(void *d_ptr);
+int tsdf_b200_fill_f32(float *d_ptr, size_t count, float value, void *stream);
 
 /* Z-sharded raycast, resolve phase: reduced keys -> vertices (NaN^3 for INT64_MAX) and optional k_hit,
  * with the hit formula of RayCaster/GPURaycaster.cu:336-348.                                        */

@@ -561,3 +561,57 @@ def test_interleaved_slabs_equal_whole(G, world, slab):
     assert_bits_equal(ranks[0].vertices.cpu().numpy(), whole.vertices.cpu().numpy(), "vertices")
     assert_bits_equal(ranks[0].normals.cpu().numpy(), whole.normals.cpu().numpy(), "normals")
     assert int((~torch.isnan(whole.vertices.view(-1, 3)[:, 0])).sum()) > 5000
+
+
+@pytest.mark.parametrize("world,slab,n", [(2, 16, (96, 80, 112)), (3, 8, (96, 80, 112)), (8, 16, (96, 80, 112)), (4, 8, (90, 77, 61))])
+def test_replica_image_sharding_equals_whole(G, world, slab, n):
+    """layout="replica" (the multi-GPU path of bench.py --gpus N), ranks emulated on one GPU: every rank integrates its
+    slabs, the brick flags are max-merged (the all-reduce), every rank pushes its surface bricks into every rank's replica
+    (pre-filled with NaN here: a single voxel read outside the pushed set would poison a sample), marches its own pixel
+    tiles and stores them into every rank's vertex map.  Each rank's vertex and normal maps must equal the single-volume
+    raycast bit for bit."""
+    import ctypes as C
+    import torch
+    from tsdf_b200 import scenes, sharded
+    from tsdf_b200.capi import lib, check
+    phys = (3000.0, 2500.0, 3000.0)
+    whole = sharded.ShardedEngine(n, phys)
+    ranks = [sharded.ShardedEngine(n, phys, rank=r, world=world, layout="replica", slab=slab) for r in range(world)]
+    for e in ranks:
+        check(lib.tsdf_b200_fill_f32(C.c_void_p(e.replica), n[0] * n[1] * n[2], float("nan"), e.stream))
+        e.connect(320, 240, peers=ranks)
+    assert all(e.replicas is not None and len(e.vmaps) == world for e in ranks)
+    for frame in (0, 2, 5, 7):
+        cam = scenes.orbit_camera(frame, 12)
+        k = cam.k.copy(); k[:2] *= 0.5
+        cam.k = k
+        cam.kinv = np.linalg.inv(k.astype(np.float64)).astype(np.float32)
+        depth = torch.from_numpy(scenes.render_depth(cam, 320, 240)).cuda()
+        total = whole.integrate(depth, cam, count=True)
+        assert sum(e.integrate(depth, cam, count=True) for e in ranks) == total
+        whole.raycast(320, 240, cam)
+        merged = ranks[0].flags().clone()
+        for e in ranks[1:]:
+            merged = torch.maximum(merged, e.flags())
+        for e in ranks:
+            e.flags().copy_(merged)
+        pushed = sum(e.push(count=True) for e in ranks)
+        for e in ranks:
+            check(lib.tsdf_b200_fill_f32(C.c_void_p(e.vmap), 320 * 240 * 3, -1.0, e.stream))
+        torch.cuda.synchronize()
+        for e in ranks:
+            e.march_tiles(320, 240, cam)
+        for e in ranks:
+            e.finish(320, 240)
+        torch.cuda.synchronize()
+        flagged = int(merged.sum().item())
+        assert flagged <= pushed <= 27 * flagged and pushed <= merged.numel()
+        for e in ranks:
+            assert_bits_equal(e.vertices.cpu().numpy(), whole.vertices.cpu().numpy(), f"vertices of rank {e.rank}, frame {frame}")
+            assert_bits_equal(e.normals.cpu().numpy(), whole.normals.cpu().numpy(), f"normals of rank {e.rank}, frame {frame}")
+    assert int((~torch.isnan(whole.vertices.view(-1, 3)[:, 0])).sum()) > 5000
+    # the merged flags equal the single volume's flags: nothing a rank cannot see decides a brick
+    assert torch.equal(merged, whole.occ[:merged.numel()])
+    for e in ranks:
+        e.close()
+    whole.close()

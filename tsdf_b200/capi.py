@@ -4,7 +4,7 @@ import os
 
 import numpy as np
 
-LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libtsdf_b200.so")
+LIB_PATH = os.environ.get("TSDF_B200_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "libtsdf_b200.so")
 if not os.path.exists(LIB_PATH):
     raise ImportError(
         f"{LIB_PATH} not found: build the CUDA extension first "
@@ -42,6 +42,14 @@ SIGNATURES = {
                                          _u32, _u32, _vp, _vp, _vp, _vp, C.c_int, _vp]),
     "tsdf_b200_raycast_interleaved": (C.c_int, [_vp, _u32, _u32, _u32, _u32, _u32, _u32, _f, _f, _f, C.c_float, _f, _f, _f,
                                                 _u32, _u32, _vp, _vp, _vp, _vp, C.c_int, _vp]),
+    "tsdf_b200_bricks_push": (C.c_int, [_vp, _u32, _u32, _u32, _u32, _u32, _u32, _vp, _u32, C.POINTER(_vp), _vp, _vp]),
+    "tsdf_b200_raycast_tiles": (C.c_int, [_vp, _u32, _u32, _u32, _f, _f, _f, C.c_float, _f, _f, _f, _u32, _u32, _vp, _vp,
+                                          _u32, _u32, _u32, C.POINTER(_vp), _vp, C.c_int, _vp]),
+    "tsdf_b200_peer_alloc": (C.c_int, [C.c_size_t, C.POINTER(_vp), C.c_char_p]),
+    "tsdf_b200_peer_open": (C.c_int, [C.c_char_p, C.POINTER(_vp)]),
+    "tsdf_b200_peer_close": (C.c_int, [_vp]),
+    "tsdf_b200_peer_free": (C.c_int, [_vp]),
+    "tsdf_b200_fill_f32": (C.c_int, [_vp, C.c_size_t, C.c_float, _vp]),
     "tsdf_b200_raycast_resolve": (C.c_int, [_vp, _f, _f, C.c_float, _f, _f, _f, _u32, _u32, _vp, _vp, _vp, _vp]),
     "tsdf_b200_normals": (C.c_int, [_u32, _u32, _vp, _vp, _vp]),
     "tsdf_b200_selftest_division": (C.c_int, [C.c_float, _ull]),

@@ -43,6 +43,11 @@ struct RayParams {
     unsigned long long *n_samples;
     unsigned int *tile_counter;  // work counter for dynamic tile scheduling (zeroed before the launch) or nullptr
     int debug_iters;             // TSDF_B200_DEBUG_ITERS: khit receives loop iterations per ray (tuning aid)
+    // Image sharding (tsdf_b200_raycast_tiles): of every `tile_stride` consecutive tiles this rank (tile_first) marches one,
+    // and stores each vertex into all n_out vertex maps (its own and, through peer memory, the other GPUs')
+    uint32_t tile_first, tile_stride;
+    uint32_t n_out;
+    float *out[TSDF_B200_MAX_PEERS];
 };
 
 template <bool FASTDIV>
@@ -176,6 +181,7 @@ raycast_kernel(const __grid_constant__ RayParams P) {
     const int lane = threadIdx.x & 31;
     const uint32_t tiles_x = (P.width + 7) / 8, tiles_y = (P.height + 3) / 4, n_tiles = tiles_x * tiles_y;
     const uint32_t warps_total = gridDim.x * (blockDim.x >> 5);
+    const uint32_t n_work = P.tile_stride > 1 ? (n_tiles + P.tile_stride - 1) / P.tile_stride : n_tiles;
     uint32_t samples = 0;
     auto next_tile = [&](uint32_t previous, bool first) -> uint32_t {
         if (!P.tile_counter) return first ? blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5) : previous + warps_total;
@@ -184,7 +190,15 @@ raycast_kernel(const __grid_constant__ RayParams P) {
         return __shfl_sync(0xffffffffu, t, 0);
     };
 
-    for (uint32_t tile = next_tile(0, true); tile < n_tiles; tile = next_tile(tile, false)) {
+    for (uint32_t work = next_tile(0, true); work < n_work; work = next_tile(work, false)) {
+    uint32_t tile = work;
+    if (P.tile_stride > 1) {
+        // one tile of each group of tile_stride; the pick rotates from tile row to tile row so that a rank's tiles do
+        // not line up in image columns
+        const uint32_t base = tile * P.tile_stride;
+        tile = base + (P.tile_first + base / tiles_x) % P.tile_stride;
+        if (tile >= n_tiles) continue;
+    }
     const uint32_t imx = (tile % tiles_x) * 8 + (lane & 7);
     const uint32_t imy = (tile / tiles_x) * 4 + (lane >> 3);
     if (imx < P.width && imy < P.height) {
@@ -193,6 +207,11 @@ raycast_kernel(const __grid_constant__ RayParams P) {
         float ip[3] = { CUDART_NAN_F, CUDART_NAN_F, CUDART_NAN_F };
         int kh = -1, dbg_iters = 0;
         float s_hit = 0.0f;
+#ifdef TSDF_RAY_DEBUG
+        int dbg_l1 = 0, dbg_l2 = 0, dbg_eval = 0, dbg_l3 = 0;
+        unsigned long long dbg_t0;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(dbg_t0));
+#endif
 
         if (R.intersects) {
             const float *dir = R.dir, *start = R.start;
@@ -306,6 +325,9 @@ raycast_kernel(const __grid_constant__ RayParams P) {
                         }
                         if (off_low_edge && (cd >= 2 || clear)) {
                             k += 1 + safe_steps(s_t, k, t, t_gain, inv_step);
+#ifdef TSDF_RAY_DEBUG
+                            dbg_l1++;
+#endif
                             continue;
                         }
                     }
@@ -422,8 +444,14 @@ raycast_kernel(const __grid_constant__ RayParams P) {
                             t_gain = fminf(t_gain, (dlo >= 0.0f && dhi >= 0.0f) ? ta : -1.0f);
                         }
                         k += 1 + safe_steps(s_t, k, t, t_gain, inv_step);
+#ifdef TSDF_RAY_DEBUG
+                        dbg_l2++;
+#endif
                         continue;
                     }
+#ifdef TSDF_RAY_DEBUG
+                    dbg_eval++;
+#endif
 
                     const float u1 = fsub(1.0f, u), v1 = fsub(1.0f, v), w1 = fsub(1.0f, w);
                     s = fmul(fmul(fmul(c000, u1), v1), w1);                                      // :114-121
@@ -460,15 +488,36 @@ raycast_kernel(const __grid_constant__ RayParams P) {
                             t_gain = fminf(t_gain, (dlo >= 0.0f && dhi >= 0.0f) ? ta : -1.0f);
                         }
                         k += min(j, safe_steps(s_t, k, t, t_gain, inv_step));
+#ifdef TSDF_RAY_DEBUG
+                        dbg_l3 += 1;
+#endif
                     }
                 }
                 k++;
             }
             dbg_iters = iters;
         }
+#ifdef TSDF_RAY_DEBUG
+        {
+            unsigned long long dbg_t1;
+            __syncwarp(__activemask());
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(dbg_t1));
+            if (P.debug_iters == 2) dbg_iters = dbg_eval;
+            if (P.debug_iters == 3) dbg_iters = dbg_l1;
+            if (P.debug_iters == 4) dbg_iters = dbg_l2;
+            if (P.debug_iters == 5) dbg_iters = (int)(dbg_t1 - dbg_t0);
+            if (P.debug_iters == 6) dbg_iters = (int)(dbg_t0 & 0x7fffffffull);
+            if (P.debug_iters == 7) dbg_iters = dbg_l3;
+        }
+#endif
         if (SLAB) {
             // key: first hit along the ray wins an all-reduce(min); the sample value rides in the low word
             P.keys[pix] = (kh >= 0) ? (((long long)kh << 32) | (long long)(uint32_t)__float_as_uint(s_hit)) : 0x7fffffffffffffffLL;
+        } else if (P.n_out) {
+            for (uint32_t d = 0; d < P.n_out; d++) {
+                float *v = P.out[d] + 3 * pix;
+                v[0] = ip[0]; v[1] = ip[1]; v[2] = ip[2];
+            }
         } else {
             P.vertices[3 * pix + 0] = ip[0];
             P.vertices[3 * pix + 1] = ip[1];
@@ -491,6 +540,11 @@ resolve_kernel(const __grid_constant__ RayParams P) {
     const uint32_t imx = blockIdx.x * 16 + (threadIdx.x & 15);
     const uint32_t imy = blockIdx.y * 8 + (threadIdx.x >> 4);
     if (imx >= P.width || imy >= P.height) return;
+    if (P.tile_stride > 1) {       // image sharding: only the pixels of this rank's tiles (same pick as the march)
+        const uint32_t tiles_x = (P.width + 7) / 8, tile = (imy / 4) * tiles_x + imx / 8;
+        const uint32_t base = tile / P.tile_stride * P.tile_stride;
+        if (tile != base + (P.tile_first + base / tiles_x) % P.tile_stride) return;
+    }
     const size_t pix = (size_t)imy * P.width + imx;
     const long long key = P.keys[pix];
     float ip[3] = { CUDART_NAN_F, CUDART_NAN_F, CUDART_NAN_F };
@@ -500,6 +554,13 @@ resolve_kernel(const __grid_constant__ RayParams P) {
         const float s = __uint_as_float((uint32_t)(key & 0xffffffffLL));
         const RaySetup R = ray_setup(P, imx, imy);
         hit_vertex(P, R, __ldg(P.table + kh), s, ip);
+    }
+    if (P.n_out) {
+        for (uint32_t d = 0; d < P.n_out; d++) {
+            float *v = P.out[d] + 3 * pix;
+            v[0] = ip[0]; v[1] = ip[1]; v[2] = ip[2];
+        }
+        return;
     }
     P.vertices[3 * pix + 0] = ip[0];
     P.vertices[3 * pix + 1] = ip[1];
@@ -606,8 +667,9 @@ static int fill_params(RayParams &P, const float *d_dist, uint32_t nx, uint32_t 
     P.z_base = 0; P.z_lo = 0; P.z_hi = nz;
     P.cyc_s = 0; P.cyc_g = 0; P.cyc_r = 0;
     P.vertices = nullptr; P.khit = nullptr; P.keys = nullptr; P.n_samples = nullptr; P.tile_counter = nullptr;
-    static const int dbg = getenv("TSDF_B200_DEBUG_ITERS") ? atoi(getenv("TSDF_B200_DEBUG_ITERS")) : 0;
-    P.debug_iters = dbg;
+    P.debug_iters = getenv("TSDF_B200_DEBUG_ITERS") ? atoi(getenv("TSDF_B200_DEBUG_ITERS")) : 0;
+    P.tile_first = 0; P.tile_stride = 1; P.n_out = 0;
+    for (int i = 0; i < TSDF_B200_MAX_PEERS; i++) P.out[i] = nullptr;
     return 0;
 }
 
@@ -631,7 +693,8 @@ static int launch_march(RayParams &P, int fastdiv, cudaStream_t s) {
         }
     }
     dim3 block(128);
-    const uint32_t n_tiles = ((P.width + 7) / 8) * ((P.height + 3) / 4);
+    uint32_t n_tiles = ((P.width + 7) / 8) * ((P.height + 3) / 4);
+    if (P.tile_stride > 1) n_tiles = (n_tiles + P.tile_stride - 1) / P.tile_stride;      // tiles this rank marches
     auto launch = [&](auto kernel) -> int {
         // resident blocks on this device (queried once per kernel variant)
         static int resident = 0;
@@ -664,6 +727,31 @@ extern "C" int tsdf_b200_raycast_ex(const float *d_dist, uint32_t nx, uint32_t n
     const BrickDims nb = brick_dims(nx, ny, nz);
     P.nbx = nb.bx; P.nby = nb.by; P.nbz = nb.bz;
     P.vertices = d_vertices; P.khit = d_khit; P.n_samples = d_n_samples;
+    return launch_march<false>(P, fastdiv, (cudaStream_t)stream);
+}
+
+extern "C" int tsdf_b200_raycast_tiles(const float *d_dist, uint32_t nx, uint32_t ny, uint32_t nz,
+                                       const float voxel[3], const float space_min[3], const float space_max[3],
+                                       float trunc, const float origin[3], const float rot[9], const float kinv[9],
+                                       uint32_t width, uint32_t height, const float *d_table,
+                                       const uint8_t *d_occ, uint32_t world, uint32_t rank,
+                                       uint32_t n_out, float *const *d_vertices_out,
+                                       unsigned long long *d_n_samples, int fastdiv, void *stream) {
+    if (!d_dist || !d_vertices_out || n_out == 0 || n_out > TSDF_B200_MAX_PEERS || world == 0 || rank >= world)
+        return TSDF_B200_EINVAL;
+    RayParams P;
+    int rc = fill_params(P, d_dist, nx, ny, nz, voxel, space_min, space_max, trunc, origin, rot, kinv, width, height, d_table, &fastdiv);
+    if (rc) return rc;
+    P.occ = d_occ;
+    const BrickDims nb = brick_dims(nx, ny, nz);
+    P.nbx = nb.bx; P.nby = nb.by; P.nbz = nb.bz;
+    P.n_samples = d_n_samples;
+    P.tile_first = rank; P.tile_stride = world;
+    P.n_out = n_out;
+    for (uint32_t i = 0; i < n_out; i++) {
+        if (!d_vertices_out[i]) return TSDF_B200_EINVAL;
+        P.out[i] = d_vertices_out[i];
+    }
     return launch_march<false>(P, fastdiv, (cudaStream_t)stream);
 }
 

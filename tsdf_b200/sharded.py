@@ -9,9 +9,15 @@ rays through the samples whose interpolation cell starts in its slab and emits, 
 (t_k is ray-independent, so the winning (k, sample) reproduces the single-GPU vertex bit for bit);
 every rank then resolves keys to vertices and normals.
 
+layout="replica" (world > 1) shards the IMAGE instead: slabs are dealt round robin, every rank pushes the surface bricks
+it owns into a full-size copy of the distance volume on every GPU (peer stores over NVLink, tsdf_b200_bricks_push), then
+marches its own pixel tiles with the single-GPU kernel and stores the vertices into every GPU's vertex map
+(tsdf_b200_raycast_tiles).  Collectives: a max-reduce of the brick flags and two barriers per frame.
+
 PyTorch provides device memory, the stream and torch.distributed — nothing else.
 """
 import ctypes as C
+import os
 
 import numpy as np
 import torch
@@ -38,6 +44,24 @@ def _ptr(t):
     return C.c_void_p(t.data_ptr()) if t is not None else None
 
 
+class _RawF32:
+    """A raw device pointer dressed for torch.as_tensor (peer-shareable cudaMalloc blocks are not torch allocations)."""
+
+    def __init__(self, ptr, count):
+        self.__cuda_array_interface__ = {"shape": (count,), "typestr": "<f4", "data": (int(ptr), False), "version": 2}
+
+
+def _peer_alloc(count):
+    p = C.c_void_p()
+    h = C.create_string_buffer(64)
+    check(lib.tsdf_b200_peer_alloc(count * 4, C.byref(p), h), "peer_alloc")
+    return p.value, h.raw
+
+
+def _ptr_array(ptrs):
+    return (C.c_void_p * len(ptrs))(*ptrs)
+
+
 class ShardedEngine:
     def __init__(self, n, physical, rank=0, world=1, stream=None, skipping=True, stage_depth=True, layout="contiguous", slab=16):
         """layout (world > 1): "contiguous" — one slab per rank (default); "interleaved" — global slabs of `slab` planes
@@ -57,7 +81,7 @@ class ShardedEngine:
         nz = self.n[2]
         self.layout = layout if world > 1 else "contiguous"
         self.slab = slab
-        if self.layout == "interleaved":
+        if self.layout in ("interleaved", "replica"):
             assert slab % BRICK == 0
             self.slabs = interleaved_slabs(nz, world, rank, slab)          # [(z0, z1)] owned, each stored with a halo plane
             planes = max(len(self.slabs), 1) * (slab + 1)
@@ -84,16 +108,26 @@ class ShardedEngine:
             check(lib.tsdf_b200_selftest_division(np.float32(b), C.byref(bad)), "selftest_division")
             if bad.value:
                 self.fastdiv = 0
+        self.replica = None
+        self._opened = []
+        if self.layout == "replica":
+            # full-size copy of the distance volume; only surface bricks are ever written (by every rank's push) or read
+            self.replica, self.replica_handle = _peer_alloc(self.n[0] * self.n[1] * self.n[2])
+            check(lib.tsdf_b200_fill_f32(C.c_void_p(self.replica), self.n[0] * self.n[1] * self.n[2], self.trunc, self.stream), "fill")
+            self.replicas = None          # every rank's replica as seen from this process, in rank order (connect())
+            self.vmaps = None
+            self.vmap = None
+            self._token = torch.zeros(1, dtype=torch.int32, device="cuda")
         self.clear()
         # kernels per step: 2 pyramid launches (depth staging) + integrate (+ halo integrate when sharded) + 3
         # brick-distance passes + raycast + normals (+ resolve when sharded; the all-reduce is NCCL's)
         self.launches_per_step = (6 if world == 1 else 8) + (2 if stage_depth else 0)
-        if self.layout == "interleaved":
+        if self.layout in ("interleaved", "replica"):
             self.launches_per_step += 2 * (len(self.slabs) - 1)          # one integrate + one halo integrate per owned slab
 
     # ------------------------------------------------------------------------------------------
     def clear(self):
-        if self.layout == "interleaved":
+        if self.layout in ("interleaved", "replica"):
             check(lib.tsdf_b200_clear(_ptr(self.dist), _ptr(self.weight), *self.local_n, self.trunc, None, self.stream), "clear")
             self.occ.zero_()
         else:
@@ -140,7 +174,7 @@ class ShardedEngine:
                 self.stage(d_depth)
             staged = _ptr(self._staged)
         cnt = C.c_void_p(self.counters.data_ptr()) if count else None
-        if self.layout == "interleaved":
+        if self.layout in ("interleaved", "replica"):
             nx, ny, nz = self.n
             plane = nx * ny
             bricks_per_layer = ((nx + BRICK - 1) // BRICK) * ((ny + BRICK - 1) // BRICK)
@@ -205,7 +239,92 @@ class ShardedEngine:
                                             kinv_p, w, h, _ptr(self.table), _ptr(self.vertices), None, self.stream), "resolve")
         check(lib.tsdf_b200_normals(w, h, _ptr(self.vertices), _ptr(self.normals), self.stream), "normals")
 
+    # ---- layout="replica": image-sharded raycast over peer memory ------------------------------------------------------
+    def connect(self, w, h, peers=None):
+        """Allocates this rank's shareable vertex map and learns every rank's replica and vertex map.  peers: the engines
+        of all ranks when they live in this process (tests emulate the ranks on one GPU); otherwise the CUDA IPC handles
+        travel through torch.distributed (collective call)."""
+        if self.vmap is None or self._pix != w * h:
+            self._pix = w * h
+            self.vmap, self.vmap_handle = _peer_alloc(w * h * 3)
+            self.vertices = torch.as_tensor(_RawF32(self.vmap, w * h * 3), device="cuda")
+            self.normals = torch.empty(w * h * 3, dtype=torch.float32, device="cuda")
+            self.replicas = None
+        if self.replicas is not None:
+            return
+        if peers is not None:
+            if any(e.vmap is None or e._pix != w * h for e in peers):
+                return                                      # the last engine to allocate completes everyone's lists
+            for e in peers:
+                e.replicas = [q.replica for q in peers]
+                e.vmaps = [q.vmap for q in peers]
+            return
+        import torch.distributed as dist
+        handles = [None] * self.world
+        dist.all_gather_object(handles, (self.replica_handle, self.vmap_handle))
+        self.replicas, self.vmaps = [], []
+        for r, (hr, hv) in enumerate(handles):
+            if r == self.rank:
+                self.replicas.append(self.replica)
+                self.vmaps.append(self.vmap)
+                continue
+            for hnd, out in ((hr, self.replicas), (hv, self.vmaps)):
+                p = C.c_void_p()
+                check(lib.tsdf_b200_peer_open(hnd, C.byref(p)), "peer_open")
+                self._opened.append(p.value)
+                out.append(p.value)
+
+    def flags(self):
+        """The brick flags of the whole volume (first third of the occupancy buffer): what the ranks max-reduce."""
+        nb = ((self.n[0] + BRICK - 1) // BRICK) * ((self.n[1] + BRICK - 1) // BRICK) * ((self.n[2] + BRICK - 1) // BRICK)
+        return self.occ[:nb]
+
+    def push(self, count=False):
+        """Copies the owned surface bricks into every rank's replica (flags must be merged first)."""
+        if count:
+            self.counters[1] = 0
+        cnt = C.c_void_p(self.counters.data_ptr() + 8) if count else None
+        check(lib.tsdf_b200_bricks_push(_ptr(self.dist), *self.n, self.slab, self.world, self.rank, _ptr(self.occ),
+                                        len(self.replicas), _ptr_array(self.replicas), cnt, self.stream), "bricks_push")
+        if count:
+            return int(self.counters[1].item())
+        return None
+
+    def march_tiles(self, w, h, cam, count=False):
+        """Marches this rank's pixel tiles against its replica and stores the vertices into every rank's vertex map."""
+        _, _, kinv_p, origin_p, rot_p, _ = self._mats(cam)
+        smin = self.offset.copy()
+        smax = (self.offset + self.physical).astype(np.float32)
+        cnt = C.c_void_p(self.counters.data_ptr() + 8) if count else None
+        check(lib.tsdf_b200_raycast_tiles(C.c_void_p(self.replica), *self.n, fptr(self.voxel), fptr(smin), fptr(smax), self.trunc,
+                                          origin_p, rot_p, kinv_p, w, h, _ptr(self.table), _ptr(self.occ) if self.skipping else None,
+                                          self.world, self.rank, len(self.vmaps), _ptr_array(self.vmaps), cnt, self.fastdiv,
+                                          self.stream), "raycast_tiles")
+
+    def finish(self, w, h):
+        check(lib.tsdf_b200_normals(w, h, _ptr(self.vertices), _ptr(self.normals), self.stream), "normals")
+
+    def _barrier(self):
+        import torch.distributed as dist
+        dist.all_reduce(self._token)          # stream-ordered; the host does not wait
+
     def raycast(self, w, h, cam, count=False):
+        if self.layout == "replica":
+            import torch.distributed as dist
+            self.connect(w, h)
+            # every rank has left the previous frame's march (it reads the replicas) before anyone's push can start:
+            # the reduction cannot complete on a rank before all ranks have entered it
+            dist.all_reduce(self.flags(), op=dist.ReduceOp.MAX)
+            self.push()
+            self._barrier()                   # all pushes have landed
+            if count:
+                self.counters[1] = 0
+            self.march_tiles(w, h, cam, count)
+            self._barrier()                   # all vertex tiles have landed
+            self.finish(w, h)
+            if count:
+                return int(self.counters[1].item())
+            return None
         self._buffers(w, h)
         if count:
             self.counters[1] = 0
@@ -277,6 +396,16 @@ class ShardedEngine:
         return self.dist.cpu().numpy(), self.weight.cpu().numpy()
 
     def close(self):
+        torch.cuda.synchronize()
+        for p in self._opened:
+            lib.tsdf_b200_peer_close(C.c_void_p(p))
+        self._opened = []
+        if self.replica is not None:
+            self.vertices = None
+            lib.tsdf_b200_peer_free(C.c_void_p(self.replica))
+            if self.vmap is not None:
+                lib.tsdf_b200_peer_free(C.c_void_p(self.vmap))
+            self.replica = self.vmap = None
         for name in ("dist", "weight", "occ", "vertices", "normals", "keys"):
             if hasattr(self, name):
                 setattr(self, name, None)

@@ -42,6 +42,14 @@ struct RayParams {
     long long *keys;
     unsigned long long *n_samples;
     unsigned int *tile_counter;  // work counter for dynamic tile scheduling (zeroed before the launch) or nullptr
+    // Continuation queue: the kernel's run time used to be the march of its slowest ray (~400 dependent loop iterations
+    // at ~1.3 us each against a median of ~25, tools/ray_iters.py).  A ray still marching after max_iters iterations
+    // appends (pixel, next sample) here and continue_kernel finishes it with a whole warp, each lane on 1/32 of the
+    // remaining samples.
+    int2 *queue;
+    unsigned int *queue_count;
+    uint32_t queue_cap;
+    int max_iters;
     int debug_iters;             // TSDF_B200_DEBUG_ITERS: khit receives loop iterations per ray (tuning aid)
     // Image sharding (tsdf_b200_raycast_tiles): of every `tile_stride` consecutive tiles this rank (tile_first) marches one,
     // and stores each vertex into all n_out vertex maps (its own and, through peer memory, the other GPUs')
@@ -164,10 +172,311 @@ __device__ __forceinline__ int safe_steps(const float *s_t, int k, float t, floa
     return j;
 }
 
+// The march of one ray over samples [k_first, k_last] (further narrowed to the slab's parameter interval when SLAB).
+// Returns -1 when the range is finished (kh >= 0: first sample <= 0 and its value), or, after max_iters loop iterations,
+// the sample to resume from.  Every sample that is evaluated uses the reference's operation order; everything else only
+// decides which samples need no evaluation.
+struct RayDebug { int iters, l1, l2, l3, eval; };
+
+template <bool FASTDIV, bool SKIP, bool SLAB>
+__device__ __forceinline__ int march_ray(const RayParams &P, const float *s_t, const RaySetup &R, int k_first, int k_last,
+                                         int max_iters, int &kh, float &s_hit, uint32_t &samples, RayDebug &dbg) {
+    const float *dir = R.dir, *start = R.start;
+    const float max_t = R.max_t;
+    const float step = P.step;
+    const float mx[3] = { fmul((float)P.nx, P.vs[0]), fmul((float)P.ny, P.vs[1]), fmul((float)P.nz, P.vs[2]) };
+    const float hi_adj[3] = { fsub(mx[0], fdiv(P.vs[0], 10.0f)), fsub(mx[1], fdiv(P.vs[1], 10.0f)), fsub(mx[2], fdiv(P.vs[2], 10.0f)) };
+    const float inv_step = __frcp_rn(step);
+    // Skipping helpers (approximate arithmetic, only ever used conservatively):
+    //   ainv = 1/|dir|, dtb = parameter length of one brick
+    float ainv[3], dtb[3];
+    int sgn[3];
+    if (SKIP) {
+#pragma unroll
+        for (int a = 0; a < 3; a++) {
+            const float ad = fabsf(dir[a]);
+            const bool moving = ad > 0.0f && ad < 3.0e38f;
+            ainv[a] = moving ? __frcp_rn(ad) : 0.0f;
+            sgn[a] = !moving ? 0 : (dir[a] > 0.0f ? 1 : -1);
+            dtb[a] = moving ? (float)TSDF_B200_BRICK * P.vs[a] * ainv[a] : 3.0e30f;
+        }
+    }
+
+    int clx = -1, cly = -1, clz = -1;     // corner cache key
+    float c000 = 0, c001 = 0, c010 = 0, c011 = 0, c100 = 0, c101 = 0, c110 = 0, c111 = 0;
+    bool cpos = false;                    // all 8 cached corners inside the positive band
+    float lip_inv = 0.0f, lip_margin = 3.0e38f;   // level 3: 1 / (Lipschitz bound per step), absolute slack
+
+    int k = k_first, k_stop = k_last;
+    if (SLAB && P.cyc_g == 0) {
+        // Parameter interval in which a sample's cell can start inside [z_lo, z_hi), with a voxel of slack.
+        const float zl = (P.z_lo == 0) ? -3.0e38f : ((float)P.z_lo - 1.0f) * P.vs[2];
+        const float zh = (P.z_hi >= P.nz) ? 3.0e38f : ((float)P.z_hi + 1.5f) * P.vs[2];
+        float ta = 0.0f, tb = 3.0e38f;
+        if (dir[2] > 0.0f)      { ta = (zl - start[2]) / dir[2]; tb = (zh - start[2]) / dir[2]; }
+        else if (dir[2] < 0.0f) { ta = (zh - start[2]) / dir[2]; tb = (zl - start[2]) / dir[2]; }
+        else if (start[2] < zl || start[2] > zh) { tb = -1.0f; }
+        if (tb < 0.0f) k = k_stop + 1;                       // never inside this slab
+        else {
+            if (ta > 0.0f && ta < 1.0e9f) {
+                int ka = (int)(ta * inv_step) - 3;
+                if (ka > k_stop) ka = k_stop + 1;
+                while (ka > 0 && ka <= k_stop && s_t[ka] > ta) ka--;
+                if (ka > k) k = ka;
+            }
+            if (tb < 1.0e9f) {
+                int kb = (int)(tb * inv_step) + 4;
+                if (kb < k_stop) k_stop = kb;
+            }
+        }
+    }
+
+    int iters = 0, resume = -1;
+    while (true) {
+        iters++;
+        if (k > k_stop) break;
+        const float t = s_t[k];
+        if (k > 0 && t >= max_t) break;                         // sample k>0 exists only if t_k < max_t (:360-365)
+        if (iters > max_iters) { resume = k; break; }           // the rest of this ray goes to the continuation queue
+
+        float p[3];
+#pragma unroll
+        for (int a = 0; a < 3; a++) p[a] = fadd(fmul(dir[a], t), start[a]);        // :326
+
+        // trilinearly_interpolate (:53-124)
+        int vox[3];
+#pragma unroll
+        for (int a = 0; a < 3; a++) {
+            float adj = p[a];
+            if (p[a] >= mx[a]) adj = hi_adj[a];
+            if (p[a] < 0.0f) adj = 0.0f;
+            vox[a] = f2i(floorf(div_vs<FASTDIV>(adj, P.vs[a], P.rvs[a])));
+        }
+        const bool oob = vox[0] < 0 || vox[1] < 0 || vox[2] < 0 ||
+                         (uint32_t)vox[0] >= P.nx || (uint32_t)vox[1] >= P.ny || (uint32_t)vox[2] >= P.nz;
+
+        // ---- level 1: empty space, sphere-traced on the brick distance grid -----------------------------
+        // cd[B] = Chebyshev distance (in bricks, capped) from brick B to the nearest brick whose voxels or
+        // 1-voxel apron leave the positive band.  A sample's fp32 position is within ~1e-3 mm of the real
+        // line start + t*dir, i.e. in the brick the real line is in or in a face/edge/corner neighbour of it.
+        //   cd >= 2: while the real line stays within cd-2 bricks of B (per axis), every sample on it lies in
+        //            a brick at distance <= cd-1 of B, hence empty, hence > 0 — no guard band is needed and
+        //            rays grazing brick faces are handled like any other;
+        //   cd == 1: B itself is empty but a neighbour is not: skip to the exit of B pulled in by a guard
+        //            band (2% of a voxel, >> the rounding error of a sample position), provided the landing
+        //            point is itself clear of every face by that band.
+        // Voxel layer 0 of each axis is never skipped (the reference extrapolates there, :87-99): the landing
+        // point and every skipped sample keep 1.05 voxels away from the low faces of the volume.
+        if (SKIP && !oob) {
+            const int b[3] = { vox[0] / TSDF_B200_BRICK, vox[1] / TSDF_B200_BRICK, vox[2] / TSDF_B200_BRICK };
+            const int bz_local = b[2] - ((SLAB && P.cyc_g == 0) ? (int)(P.z_base / TSDF_B200_BRICK) : 0);
+            const bool in_grid = !SLAB || (bz_local >= 0 && bz_local < (int)P.nbz);
+            const int cd = in_grid ? (int)__ldg(P.occ_d + ((size_t)bz_local * P.nby + b[1]) * P.nbx + b[0]) : 0;
+            if (cd >= 1) {
+                const float extra = (float)(cd - 2);      // whole bricks beyond the exit of B (cd >= 2)
+                float t_gain = 3.0e30f;
+                bool clear = true, off_low_edge = true;
+#pragma unroll
+                for (int a = 0; a < 3; a++) {
+                    const float lo = (float)(b[a] * TSDF_B200_BRICK) * P.vs[a];
+                    const float hi = (float)((b[a] + 1) * TSDF_B200_BRICK) * P.vs[a];
+                    const float g = 0.02f * P.vs[a];
+                    const float dlo = p[a] - lo, dhi = hi - p[a];
+                    const float dedge = p[a] - 1.05f * P.vs[a];          // distance to the guarded low edge of the volume
+                    clear = clear && dlo >= g && dhi >= g;
+                    off_low_edge = off_low_edge && dedge >= 0.0f;
+                    float ta;
+                    if (cd >= 2) ta = (sgn[a] > 0 ? dhi : dlo) * ainv[a] + extra * dtb[a];
+                    else         ta = ((sgn[a] > 0 ? dhi : dlo) - g) * ainv[a];
+                    if (sgn[a] < 0) ta = fminf(ta, dedge * ainv[a]);
+                    if (sgn[a] != 0) t_gain = fminf(t_gain, ta);
+                }
+                if (off_low_edge && (cd >= 2 || clear)) {
+                    k += 1 + safe_steps(s_t, k, t, t_gain, inv_step);
+#ifdef TSDF_RAY_DEBUG
+                    dbg.l1++;
+#endif
+                    continue;
+                }
+            }
+        }
+
+        float s;
+        bool uvw_in_cell = false;
+        float cell_lo[3] = { 0.0f, 0.0f, 0.0f };
+        if (oob) {
+            s = CUDART_NAN_F;                                                          // :77-80
+            samples++;
+        } else {
+            int low[3];
+            float uvw[3], lcs[3];
+#pragma unroll
+            for (int a = 0; a < 3; a++) {
+                const float ctr = fadd(fmul(fadd((float)vox[a], 0.5f), P.vs[a]), 0.0f);      // TSDF_utilities.cu:10-17
+                int l = (p[a] < ctr) ? vox[a] - 1 : vox[a];                               // :87-89
+                l = max(l, 0);                                                            // :92-94
+                const float lc = fadd(fmul(fadd((float)l, 0.5f), P.vs[a]), 0.0f);
+                uvw[a] = div_vs<FASTDIV>(fsub(p[a], lc), P.vs[a], P.rvs[a]);             // :98-102
+                low[a] = l;
+                lcs[a] = lc;
+            }
+            if (SLAB) {
+                bool mine;
+                if (P.cyc_g > 0) mine = ((uint32_t)low[2] / P.cyc_s) % P.cyc_g == P.cyc_r;
+                else             mine = (uint32_t)low[2] >= P.z_lo && (uint32_t)low[2] < P.z_hi;
+                if (!mine) {
+                    // another rank's cell: nothing of it is evaluated here.  Leave it the way level 2 leaves a cell
+                    // that is certainly positive (guard band, so that `lower` cannot flip) instead of one sample
+                    // at a time — with interleaved slabs a ray meets such cells at every slab boundary.
+                    float t_gain = -1.0f;
+                    if (SKIP && uvw[0] >= 0.0f && uvw[0] <= 1.0f && uvw[1] >= 0.0f && uvw[1] <= 1.0f && uvw[2] >= 0.0f && uvw[2] <= 1.0f) {
+                        t_gain = 3.0e30f;
+#pragma unroll
+                        for (int a = 0; a < 3; a++) {
+                            const float g = 0.02f * P.vs[a];
+                            const float dlo = p[a] - (lcs[a] + g), dhi = (lcs[a] + P.vs[a] - g) - p[a];
+                            const float ta = sgn[a] > 0 ? dhi * ainv[a] : (sgn[a] < 0 ? dlo * ainv[a] : ((dlo >= 0.0f && dhi >= 0.0f) ? 3.0e30f : -1.0f));
+                            t_gain = fminf(t_gain, (dlo >= 0.0f && dhi >= 0.0f) ? ta : -1.0f);
+                        }
+                    }
+                    k += 1 + (SKIP ? safe_steps(s_t, k, t, t_gain, inv_step) : 0);
+                    continue;
+                }
+            }
+            if (low[0] != clx || low[1] != cly || low[2] != clz) {
+                clx = low[0]; cly = low[1]; clz = low[2];
+                // tsdf_value_at (TSDF_utilities.cu:29-37): upper clamp, 32-bit index arithmetic
+                const uint32_t x0 = min((uint32_t)clx, P.nx - 1), x1 = min((uint32_t)clx + 1, P.nx - 1);
+                const uint32_t y0 = P.nx * min((uint32_t)cly, P.ny - 1), y1 = P.nx * min((uint32_t)cly + 1, P.ny - 1);
+                // array plane of global plane z: whole volume, contiguous slab, or interleaved slabs (+1 halo each)
+                const uint32_t zg0 = min((uint32_t)clz, P.nz - 1), zg1 = min((uint32_t)clz + 1, P.nz - 1);
+                uint32_t zl0, zl1;
+                if (SLAB && P.cyc_g > 0) {
+                    const uint32_t sg = zg0 / P.cyc_s;
+                    zl0 = (sg / P.cyc_g) * (P.cyc_s + 1u) + (zg0 - sg * P.cyc_s);
+                    zl1 = zl0 + (zg1 - zg0);                      // the halo plane follows the slab's last plane
+                } else {
+                    const uint32_t zb = SLAB ? P.z_base : 0u;
+                    zl0 = zg0 - zb; zl1 = zg1 - zb;
+                }
+                const uint32_t z0 = P.nx * P.ny * zl0, z1 = P.nx * P.ny * zl1;
+                c000 = __ldg(P.dist + (size_t)(z0 + y0 + x0));
+                c001 = __ldg(P.dist + (size_t)(z1 + y0 + x0));
+                c010 = __ldg(P.dist + (size_t)(z0 + y1 + x0));
+                c011 = __ldg(P.dist + (size_t)(z1 + y1 + x0));
+                c100 = __ldg(P.dist + (size_t)(z0 + y0 + x1));
+                c101 = __ldg(P.dist + (size_t)(z1 + y0 + x1));
+                c110 = __ldg(P.dist + (size_t)(z0 + y1 + x1));
+                c111 = __ldg(P.dist + (size_t)(z1 + y1 + x1));
+                if (SKIP) {
+                    const float cmin = fminf(fminf(fminf(c000, c001), fminf(c010, c011)), fminf(fminf(c100, c101), fminf(c110, c111)));
+                    const float cmax = fmaxf(fmaxf(fmaxf(c000, c001), fmaxf(c010, c011)), fmaxf(fmaxf(c100, c101), fmaxf(c110, c111)));
+                    const bool finite = (c000 == c000) && (c001 == c001) && (c010 == c010) && (c011 == c011) &&
+                                        (c100 == c100) && (c101 == c101) && (c110 == c110) && (c111 == c111);
+                    cpos = finite && cmin >= P.occ_lo && cmax <= P.occ_hi;
+                    // level 3 (below): the interpolant is multilinear, so with weights in [0,1] its derivative
+                    // along u is a convex combination of the four corner differences along x, and likewise for
+                    // v and w: |ds/dt| <= sum_a G_a * |dir_a| / voxel_a with G_a the largest corner difference
+                    // (not needed for a cell that level 2 skips as a whole)
+                    lip_inv = 0.0f;
+                    if (!cpos) {
+                    const float gx = fmaxf(fmaxf(fabsf(c100 - c000), fabsf(c101 - c001)), fmaxf(fabsf(c110 - c010), fabsf(c111 - c011)));
+                    const float gy = fmaxf(fmaxf(fabsf(c010 - c000), fabsf(c011 - c001)), fmaxf(fabsf(c110 - c100), fabsf(c111 - c101)));
+                    const float gz = fmaxf(fmaxf(fabsf(c001 - c000), fabsf(c011 - c010)), fmaxf(fabsf(c101 - c100), fabsf(c111 - c110)));
+                    const float lt = (gx * fabsf(dir[0]) * P.rvs[0] + gy * fabsf(dir[1]) * P.rvs[1] + gz * fabsf(dir[2]) * P.rvs[2]) * step;
+                    // per-step bound inflated by 1% (rounding of the bound itself)
+                    lip_inv = (finite && lt < 3.0e37f) ? 0.99f / fmaxf(lt, 1.0e-30f) : 0.0f;
+                    // an evaluated sample differs from the ideal interpolant at the ideal position by the rounding of
+                    // p (a few ulps of a coordinate as large as the volume: < 1e-6 * n voxels, four times the estimate)
+                    // times the gradient bound, plus ~10 roundings of terms no larger than the largest corner
+                    lip_margin = (gx + gy + gz) * (1.0e-6f * (float)(max(max(P.nx, P.ny), P.nz) + 2u)) +
+                                 1.0e-5f * fmaxf(fabsf(cmin), fabsf(cmax));
+                    }
+                }
+            }
+            const float u = uvw[0], v = uvw[1], w = uvw[2];
+            uvw_in_cell = u >= 0.0f && u <= 1.0f && v >= 0.0f && v <= 1.0f && w >= 0.0f && w <= 1.0f;
+            cell_lo[0] = lcs[0]; cell_lo[1] = lcs[1]; cell_lo[2] = lcs[2];
+
+            // ---- level 2: a cell whose 8 corners are all in the positive band ----------------------------
+            // With weights in [0,1] every product is >= 0 and one is >= corner/8 > 0, so the sample is > 0
+            // without evaluating it; the same holds for every following sample that stays inside the cell
+            // (pulled in by the guard band, so that `lower` and the weights' range cannot flip).
+            if (SKIP && cpos && uvw_in_cell) {
+                float t_gain = 3.0e30f;
+#pragma unroll
+                for (int a = 0; a < 3; a++) {
+                    const float g = 0.02f * P.vs[a];
+                    const float dlo = p[a] - (lcs[a] + g), dhi = (lcs[a] + P.vs[a] - g) - p[a];
+                    const float ta = sgn[a] > 0 ? dhi * ainv[a] : (sgn[a] < 0 ? dlo * ainv[a] : ((dlo >= 0.0f && dhi >= 0.0f) ? 3.0e30f : -1.0f));
+                    t_gain = fminf(t_gain, (dlo >= 0.0f && dhi >= 0.0f) ? ta : -1.0f);
+                }
+                k += 1 + safe_steps(s_t, k, t, t_gain, inv_step);
+#ifdef TSDF_RAY_DEBUG
+                dbg.l2++;
+#endif
+                continue;
+            }
+#ifdef TSDF_RAY_DEBUG
+            dbg.eval++;
+#endif
+
+            const float u1 = fsub(1.0f, u), v1 = fsub(1.0f, v), w1 = fsub(1.0f, w);
+            s = fmul(fmul(fmul(c000, u1), v1), w1);                                      // :114-121
+            s = fadd(s, fmul(fmul(fmul(c001, u1), v1), w));
+            s = fadd(s, fmul(fmul(fmul(c010, u1), v), w1));
+            s = fadd(s, fmul(fmul(fmul(c011, u1), v), w));
+            s = fadd(s, fmul(fmul(fmul(c100, u), v1), w1));
+            s = fadd(s, fmul(fmul(fmul(c101, u), v1), w));
+            s = fadd(s, fmul(fmul(fmul(c110, u), v), w1));
+            s = fadd(s, fmul(fmul(fmul(c111, u), v), w));
+            samples++;
+        }
+
+        if (s <= 0) {
+            kh = k;
+            s_hit = s;
+            
+            break;
+        }
+        // ---- level 3: samples that cannot have reached zero yet -----------------------------------------------
+        // While the ray stays in this cell (guard band as in level 2, so `lower` and the weights' range cannot
+        // flip) sample k+j is at least s - j * (Lipschitz bound per step) - rounding slack: the first j for which
+        // that is still positive need no evaluation.  This is what bounds the cost of a ray that skims a surface
+        // at a small positive distance for thousands of samples (one such ray used to set the kernel's run time).
+        if (SKIP && !oob && lip_inv > 0.0f) {
+            const int j = (int)fminf((s - lip_margin) * lip_inv, 5000.0f);       // NaN / negative -> 0 or less
+            if (j >= 1 && uvw_in_cell) {
+                float t_gain = 3.0e30f;
+#pragma unroll
+                for (int a = 0; a < 3; a++) {
+                    const float g = 0.02f * P.vs[a];
+                    const float dlo = p[a] - (cell_lo[a] + g), dhi = (cell_lo[a] + P.vs[a] - g) - p[a];
+                    const float ta = sgn[a] > 0 ? dhi * ainv[a] : (sgn[a] < 0 ? dlo * ainv[a] : ((dlo >= 0.0f && dhi >= 0.0f) ? 3.0e30f : -1.0f));
+                    t_gain = fminf(t_gain, (dlo >= 0.0f && dhi >= 0.0f) ? ta : -1.0f);
+                }
+                k += min(j, safe_steps(s_t, k, t, t_gain, inv_step));
+#ifdef TSDF_RAY_DEBUG
+                dbg.l3++;
+#endif
+            }
+        }
+        k++;
+    }
+    dbg.iters += iters;
+    return resume;
+}
+
 // One thread per pixel.  SLAB: the volume arrays hold planes [z_base, z_base + nz_local) of a Z-sharded volume,
 // only samples whose interpolation cell starts in [z_lo, z_hi) are evaluated, and the result is a key.
+#ifndef TSDF_RAY_ROUNDS
+#define TSDF_RAY_ROUNDS 4
+#endif
+#ifndef TSDF_RAY_MINB
+#define TSDF_RAY_MINB 6
+#endif
 template <bool FASTDIV, bool SKIP, bool SLAB>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, TSDF_RAY_MINB)
 raycast_kernel(const __grid_constant__ RayParams P) {
     __shared__ float s_t[TSDF_B200_RAY_TABLE_LEN];
     for (int i = threadIdx.x; i < TSDF_B200_RAY_TABLE_LEN; i += blockDim.x) s_t[i] = P.table[i];
@@ -207,310 +516,43 @@ raycast_kernel(const __grid_constant__ RayParams P) {
         float ip[3] = { CUDART_NAN_F, CUDART_NAN_F, CUDART_NAN_F };
         int kh = -1, dbg_iters = 0;
         float s_hit = 0.0f;
+        bool queued = false;
+        RayDebug dbg = { 0, 0, 0, 0, 0 };
 #ifdef TSDF_RAY_DEBUG
-        int dbg_l1 = 0, dbg_l2 = 0, dbg_eval = 0, dbg_l3 = 0;
         unsigned long long dbg_t0;
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(dbg_t0));
 #endif
 
         if (R.intersects) {
-            const float *dir = R.dir, *start = R.start;
-            const float max_t = R.max_t;
-            const float step = P.step;
-            const float mx[3] = { fmul((float)P.nx, P.vs[0]), fmul((float)P.ny, P.vs[1]), fmul((float)P.nz, P.vs[2]) };
-            const float hi_adj[3] = { fsub(mx[0], fdiv(P.vs[0], 10.0f)), fsub(mx[1], fdiv(P.vs[1], 10.0f)), fsub(mx[2], fdiv(P.vs[2], 10.0f)) };
-            const float inv_step = __frcp_rn(step);
-            // Skipping helpers (approximate arithmetic, only ever used conservatively):
-            //   ainv = 1/|dir|, dtb = parameter length of one brick
-            float ainv[3], dtb[3];
-            int sgn[3];
-            if (SKIP) {
-#pragma unroll
-                for (int a = 0; a < 3; a++) {
-                    const float ad = fabsf(dir[a]);
-                    const bool moving = ad > 0.0f && ad < 3.0e38f;
-                    ainv[a] = moving ? __frcp_rn(ad) : 0.0f;
-                    sgn[a] = !moving ? 0 : (dir[a] > 0.0f ? 1 : -1);
-                    dtb[a] = moving ? (float)TSDF_B200_BRICK * P.vs[a] * ainv[a] : 3.0e30f;
-                }
-            }
-
-            int clx = -1, cly = -1, clz = -1;     // corner cache key
-            float c000 = 0, c001 = 0, c010 = 0, c011 = 0, c100 = 0, c101 = 0, c110 = 0, c111 = 0;
-            bool cpos = false;                    // all 8 cached corners inside the positive band
-            float lip_inv = 0.0f, lip_margin = 3.0e38f;   // level 3: 1 / (Lipschitz bound per step), absolute slack
-
-            int k = 0, k_stop = TSDF_B200_MAX_SAMPLES - 1;     // samples k = 0..4401 exist (:369)
-            if (SLAB && P.cyc_g == 0) {
-                // Parameter interval in which a sample's cell can start inside [z_lo, z_hi), with a voxel of slack.
-                const float zl = (P.z_lo == 0) ? -3.0e38f : ((float)P.z_lo - 1.0f) * P.vs[2];
-                const float zh = (P.z_hi >= P.nz) ? 3.0e38f : ((float)P.z_hi + 1.5f) * P.vs[2];
-                float ta = 0.0f, tb = 3.0e38f;
-                if (dir[2] > 0.0f)      { ta = (zl - start[2]) / dir[2]; tb = (zh - start[2]) / dir[2]; }
-                else if (dir[2] < 0.0f) { ta = (zh - start[2]) / dir[2]; tb = (zl - start[2]) / dir[2]; }
-                else if (start[2] < zl || start[2] > zh) { tb = -1.0f; }
-                if (tb < 0.0f) k = k_stop + 1;                       // never inside this slab
-                else {
-                    if (ta > 0.0f && ta < 1.0e9f) {
-                        int ka = (int)(ta * inv_step) - 3;
-                        if (ka > k_stop) ka = k_stop + 1;
-                        while (ka > 0 && ka <= k_stop && s_t[ka] > ta) ka--;
-                        if (ka > 0) k = ka;
-                    }
-                    if (tb < 1.0e9f) {
-                        int kb = (int)(tb * inv_step) + 4;
-                        if (kb < k_stop) k_stop = kb;
-                    }
-                }
-            }
-
-            int iters = 0;
+            // a ray that is still marching after max_iters iterations hands the rest of its samples to the continuation
+            // queue (continue_kernel); with the queue full (or absent) it simply goes on
+            int first = 0, cap = P.queue ? P.max_iters : 0x7fffffff;
             while (true) {
-                iters++;
-                if (k > k_stop) break;
-                const float t = s_t[k];
-                if (k > 0 && t >= max_t) break;                         // sample k>0 exists only if t_k < max_t (:360-365)
-
-                float p[3];
-#pragma unroll
-                for (int a = 0; a < 3; a++) p[a] = fadd(fmul(dir[a], t), start[a]);        // :326
-
-                // trilinearly_interpolate (:53-124)
-                int vox[3];
-#pragma unroll
-                for (int a = 0; a < 3; a++) {
-                    float adj = p[a];
-                    if (p[a] >= mx[a]) adj = hi_adj[a];
-                    if (p[a] < 0.0f) adj = 0.0f;
-                    vox[a] = f2i(floorf(div_vs<FASTDIV>(adj, P.vs[a], P.rvs[a])));
-                }
-                const bool oob = vox[0] < 0 || vox[1] < 0 || vox[2] < 0 ||
-                                 (uint32_t)vox[0] >= P.nx || (uint32_t)vox[1] >= P.ny || (uint32_t)vox[2] >= P.nz;
-
-                // ---- level 1: empty space, sphere-traced on the brick distance grid -----------------------------
-                // cd[B] = Chebyshev distance (in bricks, capped) from brick B to the nearest brick whose voxels or
-                // 1-voxel apron leave the positive band.  A sample's fp32 position is within ~1e-3 mm of the real
-                // line start + t*dir, i.e. in the brick the real line is in or in a face/edge/corner neighbour of it.
-                //   cd >= 2: while the real line stays within cd-2 bricks of B (per axis), every sample on it lies in
-                //            a brick at distance <= cd-1 of B, hence empty, hence > 0 — no guard band is needed and
-                //            rays grazing brick faces are handled like any other;
-                //   cd == 1: B itself is empty but a neighbour is not: skip to the exit of B pulled in by a guard
-                //            band (2% of a voxel, >> the rounding error of a sample position), provided the landing
-                //            point is itself clear of every face by that band.
-                // Voxel layer 0 of each axis is never skipped (the reference extrapolates there, :87-99): the landing
-                // point and every skipped sample keep 1.05 voxels away from the low faces of the volume.
-                if (SKIP && !oob) {
-                    const int b[3] = { vox[0] / TSDF_B200_BRICK, vox[1] / TSDF_B200_BRICK, vox[2] / TSDF_B200_BRICK };
-                    const int bz_local = b[2] - ((SLAB && P.cyc_g == 0) ? (int)(P.z_base / TSDF_B200_BRICK) : 0);
-                    const bool in_grid = !SLAB || (bz_local >= 0 && bz_local < (int)P.nbz);
-                    const int cd = in_grid ? (int)__ldg(P.occ_d + ((size_t)bz_local * P.nby + b[1]) * P.nbx + b[0]) : 0;
-                    if (cd >= 1) {
-                        const float extra = (float)(cd - 2);      // whole bricks beyond the exit of B (cd >= 2)
-                        float t_gain = 3.0e30f;
-                        bool clear = true, off_low_edge = true;
-#pragma unroll
-                        for (int a = 0; a < 3; a++) {
-                            const float lo = (float)(b[a] * TSDF_B200_BRICK) * P.vs[a];
-                            const float hi = (float)((b[a] + 1) * TSDF_B200_BRICK) * P.vs[a];
-                            const float g = 0.02f * P.vs[a];
-                            const float dlo = p[a] - lo, dhi = hi - p[a];
-                            const float dedge = p[a] - 1.05f * P.vs[a];          // distance to the guarded low edge of the volume
-                            clear = clear && dlo >= g && dhi >= g;
-                            off_low_edge = off_low_edge && dedge >= 0.0f;
-                            float ta;
-                            if (cd >= 2) ta = (sgn[a] > 0 ? dhi : dlo) * ainv[a] + extra * dtb[a];
-                            else         ta = ((sgn[a] > 0 ? dhi : dlo) - g) * ainv[a];
-                            if (sgn[a] < 0) ta = fminf(ta, dedge * ainv[a]);
-                            if (sgn[a] != 0) t_gain = fminf(t_gain, ta);
-                        }
-                        if (off_low_edge && (cd >= 2 || clear)) {
-                            k += 1 + safe_steps(s_t, k, t, t_gain, inv_step);
-#ifdef TSDF_RAY_DEBUG
-                            dbg_l1++;
-#endif
-                            continue;
-                        }
-                    }
-                }
-
-                float s;
-                bool uvw_in_cell = false;
-                float cell_lo[3] = { 0.0f, 0.0f, 0.0f };
-                if (oob) {
-                    s = CUDART_NAN_F;                                                          // :77-80
-                    samples++;
-                } else {
-                    int low[3];
-                    float uvw[3], lcs[3];
-#pragma unroll
-                    for (int a = 0; a < 3; a++) {
-                        const float ctr = fadd(fmul(fadd((float)vox[a], 0.5f), P.vs[a]), 0.0f);      // TSDF_utilities.cu:10-17
-                        int l = (p[a] < ctr) ? vox[a] - 1 : vox[a];                               // :87-89
-                        l = max(l, 0);                                                            // :92-94
-                        const float lc = fadd(fmul(fadd((float)l, 0.5f), P.vs[a]), 0.0f);
-                        uvw[a] = div_vs<FASTDIV>(fsub(p[a], lc), P.vs[a], P.rvs[a]);             // :98-102
-                        low[a] = l;
-                        lcs[a] = lc;
-                    }
-                    if (SLAB) {
-                        bool mine;
-                        if (P.cyc_g > 0) mine = ((uint32_t)low[2] / P.cyc_s) % P.cyc_g == P.cyc_r;
-                        else             mine = (uint32_t)low[2] >= P.z_lo && (uint32_t)low[2] < P.z_hi;
-                        if (!mine) {
-                            // another rank's cell: nothing of it is evaluated here.  Leave it the way level 2 leaves a cell
-                            // that is certainly positive (guard band, so that `lower` cannot flip) instead of one sample
-                            // at a time — with interleaved slabs a ray meets such cells at every slab boundary.
-                            float t_gain = -1.0f;
-                            if (SKIP && uvw[0] >= 0.0f && uvw[0] <= 1.0f && uvw[1] >= 0.0f && uvw[1] <= 1.0f && uvw[2] >= 0.0f && uvw[2] <= 1.0f) {
-                                t_gain = 3.0e30f;
-#pragma unroll
-                                for (int a = 0; a < 3; a++) {
-                                    const float g = 0.02f * P.vs[a];
-                                    const float dlo = p[a] - (lcs[a] + g), dhi = (lcs[a] + P.vs[a] - g) - p[a];
-                                    const float ta = sgn[a] > 0 ? dhi * ainv[a] : (sgn[a] < 0 ? dlo * ainv[a] : ((dlo >= 0.0f && dhi >= 0.0f) ? 3.0e30f : -1.0f));
-                                    t_gain = fminf(t_gain, (dlo >= 0.0f && dhi >= 0.0f) ? ta : -1.0f);
-                                }
-                            }
-                            k += 1 + (SKIP ? safe_steps(s_t, k, t, t_gain, inv_step) : 0);
-                            continue;
-                        }
-                    }
-                    if (low[0] != clx || low[1] != cly || low[2] != clz) {
-                        clx = low[0]; cly = low[1]; clz = low[2];
-                        // tsdf_value_at (TSDF_utilities.cu:29-37): upper clamp, 32-bit index arithmetic
-                        const uint32_t x0 = min((uint32_t)clx, P.nx - 1), x1 = min((uint32_t)clx + 1, P.nx - 1);
-                        const uint32_t y0 = P.nx * min((uint32_t)cly, P.ny - 1), y1 = P.nx * min((uint32_t)cly + 1, P.ny - 1);
-                        // array plane of global plane z: whole volume, contiguous slab, or interleaved slabs (+1 halo each)
-                        const uint32_t zg0 = min((uint32_t)clz, P.nz - 1), zg1 = min((uint32_t)clz + 1, P.nz - 1);
-                        uint32_t zl0, zl1;
-                        if (SLAB && P.cyc_g > 0) {
-                            const uint32_t sg = zg0 / P.cyc_s;
-                            zl0 = (sg / P.cyc_g) * (P.cyc_s + 1u) + (zg0 - sg * P.cyc_s);
-                            zl1 = zl0 + (zg1 - zg0);                      // the halo plane follows the slab's last plane
-                        } else {
-                            const uint32_t zb = SLAB ? P.z_base : 0u;
-                            zl0 = zg0 - zb; zl1 = zg1 - zb;
-                        }
-                        const uint32_t z0 = P.nx * P.ny * zl0, z1 = P.nx * P.ny * zl1;
-                        c000 = __ldg(P.dist + (size_t)(z0 + y0 + x0));
-                        c001 = __ldg(P.dist + (size_t)(z1 + y0 + x0));
-                        c010 = __ldg(P.dist + (size_t)(z0 + y1 + x0));
-                        c011 = __ldg(P.dist + (size_t)(z1 + y1 + x0));
-                        c100 = __ldg(P.dist + (size_t)(z0 + y0 + x1));
-                        c101 = __ldg(P.dist + (size_t)(z1 + y0 + x1));
-                        c110 = __ldg(P.dist + (size_t)(z0 + y1 + x1));
-                        c111 = __ldg(P.dist + (size_t)(z1 + y1 + x1));
-                        if (SKIP) {
-                            const float cmin = fminf(fminf(fminf(c000, c001), fminf(c010, c011)), fminf(fminf(c100, c101), fminf(c110, c111)));
-                            const float cmax = fmaxf(fmaxf(fmaxf(c000, c001), fmaxf(c010, c011)), fmaxf(fmaxf(c100, c101), fmaxf(c110, c111)));
-                            const bool finite = (c000 == c000) && (c001 == c001) && (c010 == c010) && (c011 == c011) &&
-                                                (c100 == c100) && (c101 == c101) && (c110 == c110) && (c111 == c111);
-                            cpos = finite && cmin >= P.occ_lo && cmax <= P.occ_hi;
-                            // level 3 (below): the interpolant is multilinear, so with weights in [0,1] its derivative
-                            // along u is a convex combination of the four corner differences along x, and likewise for
-                            // v and w: |ds/dt| <= sum_a G_a * |dir_a| / voxel_a with G_a the largest corner difference
-                            // (not needed for a cell that level 2 skips as a whole)
-                            lip_inv = 0.0f;
-                            if (!cpos) {
-                            const float gx = fmaxf(fmaxf(fabsf(c100 - c000), fabsf(c101 - c001)), fmaxf(fabsf(c110 - c010), fabsf(c111 - c011)));
-                            const float gy = fmaxf(fmaxf(fabsf(c010 - c000), fabsf(c011 - c001)), fmaxf(fabsf(c110 - c100), fabsf(c111 - c101)));
-                            const float gz = fmaxf(fmaxf(fabsf(c001 - c000), fabsf(c011 - c010)), fmaxf(fabsf(c101 - c100), fabsf(c111 - c110)));
-                            const float lt = (gx * fabsf(dir[0]) * P.rvs[0] + gy * fabsf(dir[1]) * P.rvs[1] + gz * fabsf(dir[2]) * P.rvs[2]) * step;
-                            // per-step bound inflated by 1% (rounding of the bound itself)
-                            lip_inv = (finite && lt < 3.0e37f) ? 0.99f / fmaxf(lt, 1.0e-30f) : 0.0f;
-                            // an evaluated sample differs from the ideal interpolant at the ideal position by the rounding of
-                            // p (a few ulps of a coordinate as large as the volume: < 1e-6 * n voxels, four times the estimate)
-                            // times the gradient bound, plus ~10 roundings of terms no larger than the largest corner
-                            lip_margin = (gx + gy + gz) * (1.0e-6f * (float)(max(max(P.nx, P.ny), P.nz) + 2u)) +
-                                         1.0e-5f * fmaxf(fabsf(cmin), fabsf(cmax));
-                            }
-                        }
-                    }
-                    const float u = uvw[0], v = uvw[1], w = uvw[2];
-                    uvw_in_cell = u >= 0.0f && u <= 1.0f && v >= 0.0f && v <= 1.0f && w >= 0.0f && w <= 1.0f;
-                    cell_lo[0] = lcs[0]; cell_lo[1] = lcs[1]; cell_lo[2] = lcs[2];
-
-                    // ---- level 2: a cell whose 8 corners are all in the positive band ----------------------------
-                    // With weights in [0,1] every product is >= 0 and one is >= corner/8 > 0, so the sample is > 0
-                    // without evaluating it; the same holds for every following sample that stays inside the cell
-                    // (pulled in by the guard band, so that `lower` and the weights' range cannot flip).
-                    if (SKIP && cpos && uvw_in_cell) {
-                        float t_gain = 3.0e30f;
-#pragma unroll
-                        for (int a = 0; a < 3; a++) {
-                            const float g = 0.02f * P.vs[a];
-                            const float dlo = p[a] - (lcs[a] + g), dhi = (lcs[a] + P.vs[a] - g) - p[a];
-                            const float ta = sgn[a] > 0 ? dhi * ainv[a] : (sgn[a] < 0 ? dlo * ainv[a] : ((dlo >= 0.0f && dhi >= 0.0f) ? 3.0e30f : -1.0f));
-                            t_gain = fminf(t_gain, (dlo >= 0.0f && dhi >= 0.0f) ? ta : -1.0f);
-                        }
-                        k += 1 + safe_steps(s_t, k, t, t_gain, inv_step);
-#ifdef TSDF_RAY_DEBUG
-                        dbg_l2++;
-#endif
-                        continue;
-                    }
-#ifdef TSDF_RAY_DEBUG
-                    dbg_eval++;
-#endif
-
-                    const float u1 = fsub(1.0f, u), v1 = fsub(1.0f, v), w1 = fsub(1.0f, w);
-                    s = fmul(fmul(fmul(c000, u1), v1), w1);                                      // :114-121
-                    s = fadd(s, fmul(fmul(fmul(c001, u1), v1), w));
-                    s = fadd(s, fmul(fmul(fmul(c010, u1), v), w1));
-                    s = fadd(s, fmul(fmul(fmul(c011, u1), v), w));
-                    s = fadd(s, fmul(fmul(fmul(c100, u), v1), w1));
-                    s = fadd(s, fmul(fmul(fmul(c101, u), v1), w));
-                    s = fadd(s, fmul(fmul(fmul(c110, u), v), w1));
-                    s = fadd(s, fmul(fmul(fmul(c111, u), v), w));
-                    samples++;
-                }
-
-                if (s <= 0) {
-                    kh = k;
-                    s_hit = s;
-                    if (!SLAB) hit_vertex(P, R, t, s, ip);
-                    break;
-                }
-                // ---- level 3: samples that cannot have reached zero yet -----------------------------------------------
-                // While the ray stays in this cell (guard band as in level 2, so `lower` and the weights' range cannot
-                // flip) sample k+j is at least s - j * (Lipschitz bound per step) - rounding slack: the first j for which
-                // that is still positive need no evaluation.  This is what bounds the cost of a ray that skims a surface
-                // at a small positive distance for thousands of samples (one such ray used to set the kernel's run time).
-                if (SKIP && !oob && lip_inv > 0.0f) {
-                    const int j = (int)fminf((s - lip_margin) * lip_inv, 5000.0f);       // NaN / negative -> 0 or less
-                    if (j >= 1 && uvw_in_cell) {
-                        float t_gain = 3.0e30f;
-#pragma unroll
-                        for (int a = 0; a < 3; a++) {
-                            const float g = 0.02f * P.vs[a];
-                            const float dlo = p[a] - (cell_lo[a] + g), dhi = (cell_lo[a] + P.vs[a] - g) - p[a];
-                            const float ta = sgn[a] > 0 ? dhi * ainv[a] : (sgn[a] < 0 ? dlo * ainv[a] : ((dlo >= 0.0f && dhi >= 0.0f) ? 3.0e30f : -1.0f));
-                            t_gain = fminf(t_gain, (dlo >= 0.0f && dhi >= 0.0f) ? ta : -1.0f);
-                        }
-                        k += min(j, safe_steps(s_t, k, t, t_gain, inv_step));
-#ifdef TSDF_RAY_DEBUG
-                        dbg_l3 += 1;
-#endif
-                    }
-                }
-                k++;
+                first = march_ray<FASTDIV, SKIP, SLAB>(P, s_t, R, first, TSDF_B200_MAX_SAMPLES - 1, cap, kh, s_hit, samples, dbg);
+                if (first < 0) break;
+                const uint32_t slot = atomicAdd(P.queue_count, 1u);
+                if (slot < P.queue_cap) { P.queue[slot] = make_int2((int)pix, first); queued = true; break; }
+                cap = 0x7fffffff;
             }
-            dbg_iters = iters;
+            if (kh >= 0 && !SLAB) hit_vertex(P, R, s_t[kh], s_hit, ip);
+            dbg_iters = dbg.iters;
         }
 #ifdef TSDF_RAY_DEBUG
         {
             unsigned long long dbg_t1;
             __syncwarp(__activemask());
             asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(dbg_t1));
-            if (P.debug_iters == 2) dbg_iters = dbg_eval;
-            if (P.debug_iters == 3) dbg_iters = dbg_l1;
-            if (P.debug_iters == 4) dbg_iters = dbg_l2;
+            if (P.debug_iters == 2) dbg_iters = dbg.eval;
+            if (P.debug_iters == 3) dbg_iters = dbg.l1;
+            if (P.debug_iters == 4) dbg_iters = dbg.l2;
             if (P.debug_iters == 5) dbg_iters = (int)(dbg_t1 - dbg_t0);
             if (P.debug_iters == 6) dbg_iters = (int)(dbg_t0 & 0x7fffffffull);
-            if (P.debug_iters == 7) dbg_iters = dbg_l3;
+            if (P.debug_iters == 7) dbg_iters = dbg.l3;
         }
 #endif
-        if (SLAB) {
+        if (queued) {
+            // continue_kernel writes this pixel
+        } else if (SLAB) {
             // key: first hit along the ray wins an all-reduce(min); the sample value rides in the low word
             P.keys[pix] = (kh >= 0) ? (((long long)kh << 32) | (long long)(uint32_t)__float_as_uint(s_hit)) : 0x7fffffffffffffffLL;
         } else if (P.n_out) {
@@ -528,6 +570,76 @@ raycast_kernel(const __grid_constant__ RayParams P) {
     __syncwarp();
     }
 
+    if (P.n_samples) {
+        for (int o = 16; o > 0; o >>= 1) samples += __shfl_down_sync(0xffffffffu, samples, o);
+        if (lane == 0 && samples) atomicAdd(P.n_samples, (unsigned long long)samples);
+    }
+}
+
+// Finishes the rays raycast_kernel set aside: one warp per queue entry (pixel, first remaining sample), lane l marching
+// the l-th of 32 equal pieces of the remaining sample range; the ray's first hit is the smallest hit sample over the lanes.
+template <bool FASTDIV, bool SKIP, bool SLAB>
+__global__ void __launch_bounds__(128, TSDF_RAY_MINB)
+continue_kernel(const __grid_constant__ RayParams P) {
+    __shared__ float s_t[TSDF_B200_RAY_TABLE_LEN];
+    for (int i = threadIdx.x; i < TSDF_B200_RAY_TABLE_LEN; i += blockDim.x) s_t[i] = P.table[i];
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const uint32_t warps_total = gridDim.x * (blockDim.x >> 5);
+    const uint32_t n = min(*P.queue_count, P.queue_cap);
+    uint32_t samples = 0;
+    for (uint32_t e = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); e < n; e += warps_total) {
+        const int2 entry = P.queue[e];
+        const size_t pix = (size_t)entry.x;
+        const uint32_t imx = (uint32_t)entry.x % P.width, imy = (uint32_t)entry.x / P.width;
+        const RaySetup R = ray_setup(P, imx, imy);
+        // samples the ray still has: k_end is only an estimate of the last one, the final piece runs to the end of the table
+        const int k0 = entry.y;
+        const int k_end = min(max((int)fminf(R.max_t * __frcp_rn(P.step), 5000.0f) + 1, k0), TSDF_B200_MAX_SAMPLES - 1);
+        const int len = k_end - k0 + 1;
+        // The remaining samples are cut into kRounds * 32 chunks; in round r lane l marches chunk 32 r + l.  Neighbouring
+        // chunks run side by side, so a stretch of expensive samples (a ray skimming a surface) spreads over many lanes
+        // instead of landing in one lane's piece; a round whose chunks all start behind the best hit so far is skipped.
+        constexpr int kRounds = TSDF_RAY_ROUNDS, kChunks = 32 * kRounds;
+        int kh = -1;
+        float s_hit = 0.0f;
+        RayDebug dbg = { 0, 0, 0, 0, 0 };
+        long long key = 0x7fffffffffffffffLL;
+        for (int r = 0; r < kRounds; r++) {
+            const int c = 32 * r + lane;
+            const int first = k0 + (int)((long long)len * c / kChunks);
+            const int last = c == kChunks - 1 ? TSDF_B200_MAX_SAMPLES - 1 : k0 + (int)((long long)len * (c + 1) / kChunks) - 1;
+            if (first <= last && kh < 0) march_ray<FASTDIV, SKIP, SLAB>(P, s_t, R, first, last, 0x7fffffff, kh, s_hit, samples, dbg);
+            key = (kh >= 0) ? (((long long)kh << 32) | (long long)(uint32_t)__float_as_uint(s_hit)) : 0x7fffffffffffffffLL;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) key = min(key, __shfl_xor_sync(0xffffffffu, key, o));
+            if (key != 0x7fffffffffffffffLL) break;           // later rounds only hold later samples
+        }
+        if (lane == 0) {
+            if (SLAB) {
+                P.keys[pix] = key;
+            } else {
+                float ip[3] = { CUDART_NAN_F, CUDART_NAN_F, CUDART_NAN_F };
+                int k_hit = -1;
+                if (key != 0x7fffffffffffffffLL) {
+                    k_hit = (int)(key >> 32);
+                    hit_vertex(P, R, s_t[k_hit], __uint_as_float((uint32_t)(key & 0xffffffffLL)), ip);
+                }
+                if (P.n_out) {
+                    for (uint32_t d = 0; d < P.n_out; d++) {
+                        float *v = P.out[d] + 3 * pix;
+                        v[0] = ip[0]; v[1] = ip[1]; v[2] = ip[2];
+                    }
+                } else {
+                    P.vertices[3 * pix + 0] = ip[0];
+                    P.vertices[3 * pix + 1] = ip[1];
+                    P.vertices[3 * pix + 2] = ip[2];
+                    if (P.khit && !P.debug_iters) P.khit[pix] = k_hit;
+                }
+            }
+        }
+        __syncwarp();
+    }
     if (P.n_samples) {
         for (int o = 16; o > 0; o >>= 1) samples += __shfl_down_sync(0xffffffffu, samples, o);
         if (lane == 0 && samples) atomicAdd(P.n_samples, (unsigned long long)samples);
@@ -669,6 +781,9 @@ static int fill_params(RayParams &P, const float *d_dist, uint32_t nx, uint32_t 
     P.vertices = nullptr; P.khit = nullptr; P.keys = nullptr; P.n_samples = nullptr; P.tile_counter = nullptr;
     P.debug_iters = getenv("TSDF_B200_DEBUG_ITERS") ? atoi(getenv("TSDF_B200_DEBUG_ITERS")) : 0;
     P.tile_first = 0; P.tile_stride = 1; P.n_out = 0;
+    P.queue = nullptr; P.queue_count = nullptr; P.queue_cap = 0;
+    static const int cap = getenv("TSDF_B200_RAY_CAP") ? atoi(getenv("TSDF_B200_RAY_CAP")) : 96;
+    P.max_iters = cap > 0 ? cap : 0x7fffffff;
     for (int i = 0; i < TSDF_B200_MAX_PEERS; i++) P.out[i] = nullptr;
     return 0;
 }
@@ -685,17 +800,23 @@ static int launch_march(RayParams &P, int fastdiv, cudaStream_t s) {
         distance_pass_kernel<1, false><<<g, 256, 0, s>>>(cd, tmp, (int)P.nbx, (int)P.nby, (int)P.nbz);
         distance_pass_kernel<2, false><<<g, 256, 0, s>>>(tmp, cd, (int)P.nbx, (int)P.nby, (int)P.nbz);
         P.occ_d = cd;
-        // the scratch third of the buffer is free again: its first aligned word becomes the tile counter
-        uint8_t *word = (uint8_t *)(((uintptr_t)tmp + 3) & ~(uintptr_t)3);
-        if (word + 4 <= tmp + nb) {
+        // the scratch third of the buffer is free again: [tile counter | queue length | continuation queue]
+        uint8_t *word = (uint8_t *)(((uintptr_t)tmp + 7) & ~(uintptr_t)7);
+        if (word + 8 <= tmp + nb) {
             P.tile_counter = reinterpret_cast<unsigned int *>(word);
-            TSDF_CUDA_TRY(cudaMemsetAsync(P.tile_counter, 0, 4, s));
+            TSDF_CUDA_TRY(cudaMemsetAsync(P.tile_counter, 0, 8, s));
+            const size_t room = (size_t)(tmp + nb - (word + 8)) / sizeof(int2);
+            if (room >= 64 && P.max_iters != 0x7fffffff) {
+                P.queue_count = P.tile_counter + 1;
+                P.queue = reinterpret_cast<int2 *>(word + 8);
+                P.queue_cap = (uint32_t)(room < 0x7fffffffu ? room : 0x7fffffffu);
+            }
         }
     }
     dim3 block(128);
     uint32_t n_tiles = ((P.width + 7) / 8) * ((P.height + 3) / 4);
     if (P.tile_stride > 1) n_tiles = (n_tiles + P.tile_stride - 1) / P.tile_stride;      // tiles this rank marches
-    auto launch = [&](auto kernel) -> int {
+    auto launch = [&](auto kernel, auto tail_kernel) -> int {
         // resident blocks on this device (queried once per kernel variant)
         static int resident = 0;
         if (resident == 0) {
@@ -707,10 +828,13 @@ static int launch_march(RayParams &P, int fastdiv, cudaStream_t s) {
         }
         const uint32_t blocks = (n_tiles + 3) / 4 < (uint32_t)resident ? (n_tiles + 3) / 4 : (uint32_t)resident;
         kernel<<<blocks, block, 0, s>>>(P);
+        if (P.queue) tail_kernel<<<resident, block, 0, s>>>(P);
         return (int)cudaGetLastError();
     };
-    if (fastdiv) return P.occ ? launch(raycast_kernel<true, true, SLAB>) : launch(raycast_kernel<true, false, SLAB>);
-    return P.occ ? launch(raycast_kernel<false, true, SLAB>) : launch(raycast_kernel<false, false, SLAB>);
+    if (fastdiv) return P.occ ? launch(raycast_kernel<true, true, SLAB>, continue_kernel<true, true, SLAB>)
+                              : launch(raycast_kernel<true, false, SLAB>, continue_kernel<true, false, SLAB>);
+    return P.occ ? launch(raycast_kernel<false, true, SLAB>, continue_kernel<false, true, SLAB>)
+                 : launch(raycast_kernel<false, false, SLAB>, continue_kernel<false, false, SLAB>);
 }
 
 extern "C" int tsdf_b200_raycast_ex(const float *d_dist, uint32_t nx, uint32_t ny, uint32_t nz,

@@ -128,6 +128,42 @@ distance_pass_kernel(const uint8_t *__restrict__ in, uint8_t *__restrict__ out, 
     out[base] = (uint8_t)best;
 }
 
+// The same transform with the passes done in shared memory (the global version is bound by ~16 dependent L2 round trips per
+// pass): one block per z-slice does the x and y passes, one block per y-row does the z pass in place.  The x/y kernel
+// also clears the work counters of the march (two words).
+__device__ __forceinline__ int distance_scan(const uint8_t *v, int i, int pos, int len, int stride) {
+    int best = v[i];
+    for (int j = 1; j < best; j++) {
+        if (pos - j >= 0)  best = min(best, max((int)v[i - j * stride], j));
+        if (pos + j < len) best = min(best, max((int)v[i + j * stride], j));
+    }
+    return best;
+}
+
+__global__ void __launch_bounds__(1024)
+distance_xy_kernel(const uint8_t *__restrict__ flags, uint8_t *__restrict__ out, int nbx, int nby, unsigned int *counters) {
+    extern __shared__ uint8_t s_grid[];
+    const int n = nbx * nby;
+    uint8_t *a = s_grid, *b = s_grid + n;
+    const size_t base = (size_t)blockIdx.x * n;
+    if (blockIdx.x == 0 && threadIdx.x == 0 && counters) { counters[0] = 0u; counters[1] = 0u; }
+    for (int i = threadIdx.x; i < n; i += blockDim.x) a[i] = flags[base + i] ? 0 : kDistCap;
+    __syncthreads();
+    for (int i = threadIdx.x; i < n; i += blockDim.x) b[i] = (uint8_t)distance_scan(a, i, i % nbx, nbx, 1);
+    __syncthreads();
+    for (int i = threadIdx.x; i < n; i += blockDim.x) out[base + i] = (uint8_t)distance_scan(b, i, i / nbx, nby, nbx);
+}
+
+__global__ void __launch_bounds__(1024)
+distance_z_kernel(uint8_t *__restrict__ grid, int nbx, int nby, int nbz) {
+    extern __shared__ uint8_t s_grid[];
+    const int n = nbx * nbz, y = blockIdx.x;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) s_grid[i] = grid[((size_t)(i / nbx) * nby + y) * nbx + i % nbx];
+    __syncthreads();
+    for (int i = threadIdx.x; i < n; i += blockDim.x)
+        grid[((size_t)(i / nbx) * nby + y) * nbx + i % nbx] = (uint8_t)distance_scan(s_grid, i, i / nbx, nbz, nbx);
+}
+
 // Per-ray set-up shared by the march and the resolve kernel: direction, clip, start point.
 struct RaySetup { float dir[3], start[3], max_t; bool intersects; };
 
@@ -795,16 +831,25 @@ static int launch_march(RayParams &P, int fastdiv, cudaStream_t s) {
         const size_t nb = (size_t)P.nbx * P.nby * P.nbz;
         uint8_t *cd = const_cast<uint8_t *>(P.occ) + nb, *tmp = cd + nb;
         if (P.nby > 65535 || P.nbz > 65535) return TSDF_B200_EINVAL;
-        const dim3 g((P.nbx + 255) / 256, P.nby, P.nbz);
-        distance_pass_kernel<0, true><<<g, 256, 0, s>>>(P.occ, cd, (int)P.nbx, (int)P.nby, (int)P.nbz);
-        distance_pass_kernel<1, false><<<g, 256, 0, s>>>(cd, tmp, (int)P.nbx, (int)P.nby, (int)P.nbz);
-        distance_pass_kernel<2, false><<<g, 256, 0, s>>>(tmp, cd, (int)P.nbx, (int)P.nby, (int)P.nbz);
-        P.occ_d = cd;
-        // the scratch third of the buffer is free again: [tile counter | queue length | continuation queue]
+        // scratch third of the buffer: [tile counter | queue length | continuation queue]
         uint8_t *word = (uint8_t *)(((uintptr_t)tmp + 7) & ~(uintptr_t)7);
-        if (word + 8 <= tmp + nb) {
+        const bool have_words = word + 8 <= tmp + nb;
+        const size_t smem_xy = 2 * (size_t)P.nbx * P.nby, smem_z = (size_t)P.nbx * P.nbz;
+        static const bool global_passes = getenv("TSDF_B200_DIST_GLOBAL") != nullptr;      // A/B switch (tuning aid)
+        if (smem_xy <= 48 * 1024 && smem_z <= 48 * 1024 && !global_passes) {
+            distance_xy_kernel<<<P.nbz, 1024, smem_xy, s>>>(P.occ, cd, (int)P.nbx, (int)P.nby,
+                                                           have_words ? reinterpret_cast<unsigned int *>(word) : nullptr);
+            distance_z_kernel<<<P.nby, 1024, smem_z, s>>>(cd, (int)P.nbx, (int)P.nby, (int)P.nbz);
+        } else {
+            const dim3 g((P.nbx + 255) / 256, P.nby, P.nbz);
+            distance_pass_kernel<0, true><<<g, 256, 0, s>>>(P.occ, cd, (int)P.nbx, (int)P.nby, (int)P.nbz);
+            distance_pass_kernel<1, false><<<g, 256, 0, s>>>(cd, tmp, (int)P.nbx, (int)P.nby, (int)P.nbz);
+            distance_pass_kernel<2, false><<<g, 256, 0, s>>>(tmp, cd, (int)P.nbx, (int)P.nby, (int)P.nbz);
+            if (have_words) TSDF_CUDA_TRY(cudaMemsetAsync(word, 0, 8, s));
+        }
+        P.occ_d = cd;
+        if (have_words) {
             P.tile_counter = reinterpret_cast<unsigned int *>(word);
-            TSDF_CUDA_TRY(cudaMemsetAsync(P.tile_counter, 0, 8, s));
             const size_t room = (size_t)(tmp + nb - (word + 8)) / sizeof(int2);
             if (room >= 64 && P.max_iters != 0x7fffffff) {
                 P.queue_count = P.tile_counter + 1;

@@ -41,6 +41,9 @@ def parse():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--size", type=int, default=512, help="voxels per side (512 = the headline workload)")
+    ap.add_argument("--layout", default="contiguous", choices=["contiguous", "interleaved", "replica"],
+                    help="multi-GPU layout (tsdf_b200/sharded.py): Z-slabs + key all-reduce, or surface replicas + image tiles")
+    ap.add_argument("--slab", type=int, default=0, help="planes per slab for the interleaved / replica layouts (0: size / gpus)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     return ap.parse_args()
@@ -183,7 +186,8 @@ def main():
         frames.append(depth)
     d_frames = [torch.from_numpy(f).cuda() for f in frames]
 
-    eng = sharded.ShardedEngine(n, PHYS, rank, world, stream=stream.cuda_stream)
+    slab = args.slab if args.slab > 0 else max(8, (size // max(world, 1)) // 8 * 8)
+    eng = sharded.ShardedEngine(n, PHYS, rank, world, stream=stream.cuda_stream, layout=args.layout, slab=slab)
 
     def step(i, count=False):
         eng.integrate(d_frames[i], cams[i], count=count)
@@ -274,7 +278,7 @@ def main():
                "d2h_bytes_per_step": 2 * W * H * 3 * 4, "ms_per_step": e2e_ms,
                "api": "tsdf_b200_volume_integrate + tsdf_b200_volume_raycast (host buffers, synchronous)"}
         vol.close()
-    elif world > 1:
+    elif world > 1 and not args.no_e2e:
         e2e = eng.e2e(frames, cams, Wm, K, W, H)
 
     cpu_baseline = None
@@ -294,12 +298,19 @@ def main():
             "config": {"workload": f"{size}^3 volume / 3000 mm, 640x480 depth, {ORBIT_FRAMES}-frame orbit of sphere+wall "
                                    f"(BASELINE configs[2]); step = integrate + raycast + normals of one frame",
                        "cache": "volume (1 GiB dist+weight at 512^3) is larger than L2, no flush needed",
-                       "parallelism": "single GPU" if world == 1 else f"Z-slab sharding over {world} GPUs"},
+                       "parallelism": "single GPU" if world == 1 else
+                                      (f"Z-slab sharding over {world} GPUs, key all-reduce(min)" if args.layout != "replica" else
+                                       f"Z-slabs of {slab} planes over {world} GPUs, surface bricks pushed to per-GPU replicas over "
+                                       f"NVLink, image tiles sharded")},
             "clocks": clocks, "e2e": e2e, "gpu_launches": eng.launches_per_step * K,
             "roofline": roofline, "cpu_baseline": cpu_baseline, "raycast": ray_stats,
         }
         print(json.dumps(out))
     if world > 1:
+        torch.cuda.synchronize()
+        dist.barrier()
+        eng.close()
+        dist.barrier()
         dist.destroy_process_group()
 
 

@@ -79,6 +79,8 @@ SIGNATURES = {
     "tsdf_b200_volume_set_skipping": (C.c_int, [_vp, C.c_int]),
 }
 for _name, (_res, _args) in SIGNATURES.items():
+    if os.environ.get("TSDF_B200_LIB") and not hasattr(lib, _name):
+        continue                       # bisecting with an older build of the library (tuning aid)
     _fn = getattr(lib, _name)          # AttributeError here = symbol missing from the library
     _fn.restype = _res
     _fn.argtypes = _args

@@ -505,6 +505,12 @@ __device__ __forceinline__ int march_ray(const RayParams &P, const float *s_t, c
 
 // One thread per pixel.  SLAB: the volume arrays hold planes [z_base, z_base + nz_local) of a Z-sharded volume,
 // only samples whose interpolation cell starts in [z_lo, z_hi) are evaluated, and the result is a key.
+template <bool FASTDIV, bool SKIP, bool SLAB>
+__device__ __noinline__ void march_ray_cold(const RayParams &P, const float *s_t, const RaySetup &R, int k_first,
+                                            int &kh, float &s_hit, uint32_t &samples, RayDebug &dbg) {
+    march_ray<FASTDIV, SKIP, SLAB>(P, s_t, R, k_first, TSDF_B200_MAX_SAMPLES - 1, 0x7fffffff, kh, s_hit, samples, dbg);
+}
+
 #ifndef TSDF_RAY_ROUNDS
 #define TSDF_RAY_ROUNDS 4
 #endif
@@ -561,14 +567,14 @@ raycast_kernel(const __grid_constant__ RayParams P) {
 
         if (R.intersects) {
             // a ray that is still marching after max_iters iterations hands the rest of its samples to the continuation
-            // queue (continue_kernel); with the queue full (or absent) it simply goes on
-            int first = 0, cap = P.queue ? P.max_iters : 0x7fffffff;
-            while (true) {
-                first = march_ray<FASTDIV, SKIP, SLAB>(P, s_t, R, first, TSDF_B200_MAX_SAMPLES - 1, cap, kh, s_hit, samples, dbg);
-                if (first < 0) break;
+            // queue (continue_kernel); with the queue full it finishes here (out-of-line copy of the march: an outer loop
+            // around the inlined one made the compiler give up reconverging the warp inside the march, 4x the instructions)
+            const int resume = march_ray<FASTDIV, SKIP, SLAB>(P, s_t, R, 0, TSDF_B200_MAX_SAMPLES - 1,
+                                                              P.queue ? P.max_iters : 0x7fffffff, kh, s_hit, samples, dbg);
+            if (resume >= 0) {
                 const uint32_t slot = atomicAdd(P.queue_count, 1u);
-                if (slot < P.queue_cap) { P.queue[slot] = make_int2((int)pix, first); queued = true; break; }
-                cap = 0x7fffffff;
+                if (slot < P.queue_cap) { P.queue[slot] = make_int2((int)pix, resume); queued = true; }
+                else march_ray_cold<FASTDIV, SKIP, SLAB>(P, s_t, R, resume, kh, s_hit, samples, dbg);
             }
             if (kh >= 0 && !SLAB) hit_vertex(P, R, s_t[kh], s_hit, ip);
             dbg_iters = dbg.iters;

@@ -397,9 +397,13 @@ class ShardedEngine:
 
     def close(self):
         torch.cuda.synchronize()
-        for p in self._opened:
-            lib.tsdf_b200_peer_close(C.c_void_p(p))
-        self._opened = []
+        if self._opened:
+            import torch.distributed as dist
+            for p in self._opened:
+                lib.tsdf_b200_peer_close(C.c_void_p(p))
+            self._opened = []
+            if dist.is_initialized():
+                dist.barrier()                # nobody frees a block that a peer still has mapped
         if self.replica is not None:
             self.vertices = None
             lib.tsdf_b200_peer_free(C.c_void_p(self.replica))

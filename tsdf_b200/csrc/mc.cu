@@ -39,10 +39,18 @@ __device__ __forceinline__ void corner_voxel(int c, uint32_t x, uint32_t y, uint
 __device__ __forceinline__ bool cube_of(const McParams &P, unsigned long long i, uint32_t &x, uint32_t &y, uint32_t &z) {
     if (i >= P.n_cubes) return false;
     const unsigned long long slab = (unsigned long long)P.cubes_x * P.cubes_y;
-    z = (uint32_t)(i / slab) + P.cz_begin;
-    const uint32_t r = (uint32_t)(i % slab);
+    uint32_t r;
+    if (P.n_cubes <= 0xffffffffull) {           // 32-bit divisions (a 64-bit one costs ~100 instructions per cube)
+        const uint32_t i32 = (uint32_t)i, slab32 = (uint32_t)slab;
+        z = i32 / slab32;
+        r = i32 - z * slab32;
+    } else {
+        z = (uint32_t)(i / slab);
+        r = (uint32_t)(i % slab);
+    }
+    z += P.cz_begin;
     y = r / P.cubes_x;
-    x = r % P.cubes_x;
+    x = r - y * P.cubes_x;
     return true;
 }
 
@@ -90,15 +98,45 @@ mc_count_kernel(const __grid_constant__ McParams P, uint32_t *__restrict__ block
     if (threadIdx.x == 0) block_counts[blockIdx.x] = total;
 }
 
-// pass 2: exclusive scan of the block counts (one block; a few hundred thousand entries at 512^3)
+// pass 2: exclusive scan of the block counts in two levels: chunks of kScanChunk counts are scanned by one block each
+// (offsets relative to the chunk + the chunk's total), then one block scans the chunk totals; the generate pass adds the two.
+constexpr int kScanChunk = 1024;
+__global__ void __launch_bounds__(kScanChunk)
+mc_scan_chunks_kernel(const uint32_t *__restrict__ block_counts, uint32_t *__restrict__ local_offsets, uint32_t n_blocks,
+                      unsigned long long *__restrict__ chunk_totals) {
+    __shared__ uint32_t s_warp[kScanChunk / 32];
+    const uint32_t i = blockIdx.x * kScanChunk + threadIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t v = i < n_blocks ? block_counts[i] : 0u;
+    uint32_t inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= (uint32_t)o) inc += t;
+    }
+    if (lane == 31) s_warp[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+        uint32_t w = s_warp[lane], winc = w;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xffffffffu, winc, o);
+            if (lane >= (uint32_t)o) winc += t;
+        }
+        s_warp[lane] = winc - w;                                   // exclusive warp bases
+        if (lane == 31) chunk_totals[blockIdx.x] = winc;
+    }
+    __syncthreads();
+    if (i < n_blocks) local_offsets[i] = s_warp[warp] + inc - v;
+}
+
+// chunk totals -> exclusive chunk offsets (in place) and the grand total; one block, a few hundred entries at 512^3
 __global__ void __launch_bounds__(1024)
-mc_scan_kernel(const uint32_t *__restrict__ block_counts, unsigned long long *__restrict__ block_offsets, uint32_t n_blocks,
-               unsigned long long *total_out) {
+mc_scan_totals_kernel(unsigned long long *__restrict__ chunk_totals, uint32_t n_chunks, unsigned long long *total_out) {
     __shared__ unsigned long long s_part[1024];
-    const uint32_t per = (n_blocks + 1023) / 1024;
-    const uint32_t b = threadIdx.x * per, e = min(b + per, n_blocks);
+    const uint32_t per = (n_chunks + 1023) / 1024;
+    const uint32_t b = threadIdx.x * per, e = min(b + per, n_chunks);
     unsigned long long sum = 0;
-    for (uint32_t i = b; i < e; i++) sum += block_counts[i];
+    for (uint32_t i = b; i < e; i++) sum += chunk_totals[i];
     s_part[threadIdx.x] = sum;
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -108,7 +146,7 @@ mc_scan_kernel(const uint32_t *__restrict__ block_counts, unsigned long long *__
     }
     __syncthreads();
     unsigned long long run = s_part[threadIdx.x];
-    for (uint32_t i = b; i < e; i++) { block_offsets[i] = run; run += block_counts[i]; }
+    for (uint32_t i = b; i < e; i++) { const unsigned long long t = chunk_totals[i]; chunk_totals[i] = run; run += t; }
 }
 
 // interpolate (MarkAndSweepMC.cu:44-58) for one coordinate set
@@ -122,7 +160,10 @@ __device__ __forceinline__ void mc_interpolate(const float v0[3], const float v1
 
 // pass 3: vertices
 __global__ void __launch_bounds__(kMcBlock)
-mc_generate_kernel(const __grid_constant__ McParams P, const unsigned long long *__restrict__ block_offsets, float *__restrict__ vertices) {
+mc_generate_kernel(const __grid_constant__ McParams P, const uint32_t *__restrict__ block_counts,
+                   const uint32_t *__restrict__ local_offsets, const unsigned long long *__restrict__ chunk_offsets,
+                   float *__restrict__ vertices) {
+    if (block_counts[blockIdx.x] == 0) return;               // nothing in these 256 cubes (the bulk of the volume)
     __shared__ uint32_t s_warp[kMcBlock / 32];
     uint32_t x = 0, y = 0, z = 0, n = 0, type = 0;
     float w[8];
@@ -133,7 +174,7 @@ mc_generate_kernel(const __grid_constant__ McParams P, const unsigned long long 
     uint32_t total;
     const uint32_t local = block_exclusive_scan(n, s_warp, total);
     if (n == 0) return;
-    float *out = vertices + 3 * (block_offsets[blockIdx.x] + local);
+    float *out = vertices + 3 * (chunk_offsets[blockIdx.x / kScanChunk] + local_offsets[blockIdx.x] + local);
     // voxel centres of the 8 corners: centre_of_voxel_at (TSDF_utilities.cu:10-17) with the volume's offset
     float c[8][3];
 #pragma unroll
@@ -173,6 +214,12 @@ static int upload_tables() {
     TSDF_CUDA_TRY(cudaMemcpyToSymbol(c_mc_count, count, sizeof(count)));
     TSDF_CUDA_TRY(cudaMemcpyToSymbol(c_mc_tri, tri, sizeof(tri)));
     TSDF_CUDA_TRY(cudaMemcpyToSymbol(c_mc_edge, kMcEdgeCorners, sizeof(kMcEdgeCorners)));
+    // keep the scratch of tsdf_b200_mc_extract in the device's stream-ordered pool between calls
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+        unsigned long long keep = 1ull << 30;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
     if (dev < 64) done[dev] = true;
     return 0;
 }
@@ -199,16 +246,23 @@ extern "C" int tsdf_b200_mc_extract(const float *d_dist, uint32_t nx, uint32_t n
     if (n_blocks64 > 0x7fffffffull) return TSDF_B200_EINVAL;
     const uint32_t n_blocks = (uint32_t)n_blocks64;
 
-    uint32_t *d_counts = nullptr;
-    unsigned long long *d_offsets = nullptr, *d_total = nullptr;
+    // scratch from the stream-ordered pool (a cudaMalloc/cudaFree pair of this size costs milliseconds)
+    const uint32_t n_chunks = (n_blocks + kScanChunk - 1) / kScanChunk;
+    uint32_t *d_counts = nullptr, *d_local = nullptr;
+    unsigned long long *d_chunks = nullptr, *d_total = nullptr;
     float *d_vertices = nullptr;
     unsigned long long total = 0;
-    cudaError_t e = cudaMalloc(&d_counts, (size_t)n_blocks * sizeof(uint32_t));
-    if (e == cudaSuccess) e = cudaMalloc(&d_offsets, ((size_t)n_blocks + 1) * sizeof(unsigned long long));
+    const size_t scratch_bytes = 2 * (size_t)n_blocks * sizeof(uint32_t) + ((size_t)n_chunks + 1) * sizeof(unsigned long long) + 16;
+    unsigned char *d_scratch = nullptr;
+    cudaError_t e = cudaMallocAsync((void **)&d_scratch, scratch_bytes, s);
     if (e == cudaSuccess) {
-        d_total = d_offsets + n_blocks;
+        d_chunks = reinterpret_cast<unsigned long long *>(d_scratch);
+        d_total = d_chunks + n_chunks;
+        d_counts = reinterpret_cast<uint32_t *>(d_total + 1);
+        d_local = d_counts + n_blocks;
         mc_count_kernel<<<n_blocks, kMcBlock, 0, s>>>(P, d_counts);
-        mc_scan_kernel<<<1, 1024, 0, s>>>(d_counts, d_offsets, n_blocks, d_total);
+        mc_scan_chunks_kernel<<<n_chunks, kScanChunk, 0, s>>>(d_counts, d_local, n_blocks, d_chunks);
+        mc_scan_totals_kernel<<<1, 1024, 0, s>>>(d_chunks, n_chunks, d_total);
         e = cudaGetLastError();
     }
     if (e == cudaSuccess) e = cudaMemcpyAsync(&total, d_total, sizeof(total), cudaMemcpyDeviceToHost, s);
@@ -216,13 +270,12 @@ extern "C" int tsdf_b200_mc_extract(const float *d_dist, uint32_t nx, uint32_t n
     if (e == cudaSuccess && total > 0) {
         e = cudaMalloc(&d_vertices, (size_t)total * 3 * sizeof(float));
         if (e == cudaSuccess) {
-            mc_generate_kernel<<<n_blocks, kMcBlock, 0, s>>>(P, d_offsets, d_vertices);
+            mc_generate_kernel<<<n_blocks, kMcBlock, 0, s>>>(P, d_counts, d_local, d_chunks, d_vertices);
             e = cudaGetLastError();
         }
-        if (e == cudaSuccess) e = cudaStreamSynchronize(s);
     }
-    cudaFree(d_counts);
-    cudaFree(d_offsets);
+    if (d_scratch) cudaFreeAsync(d_scratch, s);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s);
     if (e != cudaSuccess) { cudaFree(d_vertices); return (int)e; }
     *d_vertices_out = d_vertices;
     *n_vertices_out = total;

@@ -348,6 +348,24 @@ class ShardedEngine:
             return int(self.counters[1].item())
         return None
 
+    def extract_mesh(self):
+        """Marching cubes of this rank's owned planes (tsdf_b200_mc_extract; the halo plane closes the cubes at the slab's
+        upper face).  Returns a (n, 3) float32 CUDA tensor: three consecutive vertices per triangle, in the reference's
+        order; the whole mesh is the concatenation over the ranks in rank order.  Contiguous layout only."""
+        assert self.layout == "contiguous"
+        own = self.z1 - self.z0
+        out = C.c_void_p()
+        count = C.c_ulonglong()
+        # cubes based in the owned planes; the call clamps the range to the stored planes minus one (a cube needs plane z+1)
+        check(lib.tsdf_b200_mc_extract(_ptr(self.dist), *self.local_n, self.z0, 0, own, fptr(self.voxel),
+                                       fptr(self.offset), C.byref(out), C.byref(count), self.stream), "mc_extract")
+        mesh = torch.empty((count.value, 3), dtype=torch.float32, device="cuda")
+        if count.value:
+            mesh.copy_(torch.as_tensor(_RawF32(out.value, count.value * 3), device="cuda").view(-1, 3))
+            torch.cuda.synchronize()
+            lib.tsdf_b200_device_free(out)
+        return mesh
+
     def last_ray_stats(self):
         """Hit pixels / NaN pixels of the last raycast (diagnostics for the bench line)."""
         if self._pix == 0:

@@ -133,6 +133,17 @@ int tsdf_b200_raycast_ex(const float *d_dist, uint32_t nx, uint32_t ny, uint32_t
                          const uint8_t *d_occ, float *d_vertices, int32_t *d_khit,
                          unsigned long long *d_n_samples, int fastdiv, void *stream);
 
+/* tsdf_b200_raycast_ex that also writes the vertex map to `mirror` while it marches: meant for pinned host memory that
+ * the device can address (the level-2 volume passes the caller's buffer when it is pinned), so that the transfer of the
+ * vertex map overlaps the march instead of following it.  Each warp writes its 8x4-pixel tile as aligned 16-byte stores;
+ * requires width % 8 == 0, height % 4 == 0 and a 16-byte aligned `mirror` (or mirror == NULL: plain raycast).        */
+int tsdf_b200_raycast_mirrored(const float *d_dist, uint32_t nx, uint32_t ny, uint32_t nz,
+                               const float voxel[3], const float space_min[3], const float space_max[3],
+                               float trunc, const float origin[3], const float rot[9], const float kinv[9],
+                               uint32_t width, uint32_t height, const float *d_table,
+                               const uint8_t *d_occ, float *d_vertices, float *mirror,
+                               unsigned long long *d_n_samples, int fastdiv, void *stream);
+
 /* Z-sharded raycast, march phase.  d_dist_slab / d_occ_slab hold z_planes planes starting at global plane
  * z_base of an nx*ny*nz volume (owned planes plus the upper halo plane).  Every ray is marched, but only
  * samples whose interpolation cell starts in [z_lo, z_hi) are evaluated.  d_keys[pixel] receives

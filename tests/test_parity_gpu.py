@@ -615,3 +615,55 @@ def test_replica_image_sharding_equals_whole(G, world, slab, n):
     for e in ranks:
         e.close()
     whole.close()
+
+
+def test_mirrored_vertex_map_in_pinned_memory(G):
+    """tsdf_b200_raycast_mirrored: the copy of the vertex map written into pinned host memory during the march (tile-wise
+    16-byte stores from raycast_kernel, single pixels from continue_kernel) equals the device vertex map bit for bit; and
+    the level-2 volume gives the same result for a pinned and for a pageable result buffer."""
+    import ctypes as C
+    import torch
+    from tsdf_b200 import scenes, sharded, Volume
+    from tsdf_b200.capi import lib, check, fptr, fvec, colmajor
+    n, phys = (96, 80, 112), (3000.0, 2500.0, 3000.0)
+    eng = sharded.ShardedEngine(n, phys)
+    vol = Volume(n, phys)
+    w, h = 320, 240
+    for frame in (0, 3, 6):
+        cam = scenes.orbit_camera(frame, 12)
+        k = cam.k.copy(); k[:2] *= 0.5
+        cam.k = k
+        cam.kinv = np.linalg.inv(k.astype(np.float64)).astype(np.float32)
+        depth = scenes.render_depth(cam, w, h)
+        eng.integrate(torch.from_numpy(depth).cuda(), cam)
+        check(lib.tsdf_b200_volume_integrate(vol._h, depth.ctypes.data, w, h, fptr(colmajor(cam.inv_pose)), fptr(colmajor(cam.k)),
+                                             fptr(colmajor(cam.kinv))))
+    eng.raycast(w, h, cam)
+    want = eng.vertices.cpu().numpy()
+    dvert = torch.empty(w * h * 3, dtype=torch.float32, device="cuda")
+    mirror = torch.full((w * h * 3,), -7.0, dtype=torch.float32).pin_memory()
+    pose = np.asarray(cam.pose, np.float32)
+    smin = eng.offset.copy()
+    smax = (eng.offset + eng.physical).astype(np.float32)
+    check(lib.tsdf_b200_raycast_mirrored(C.c_void_p(eng.dist.data_ptr()), *n, fptr(eng.voxel), fptr(smin), fptr(smax), eng.trunc,
+                                         fptr(fvec(pose[:3, 3])), fptr(colmajor(pose[:3, :3])), fptr(colmajor(cam.kinv)), w, h,
+                                         C.c_void_p(eng.table.data_ptr()), C.c_void_p(eng.occ.data_ptr()), C.c_void_p(dvert.data_ptr()),
+                                         C.c_void_p(mirror.data_ptr()), None, eng.fastdiv, eng.stream), "raycast_mirrored")
+    torch.cuda.synchronize()
+    assert_bits_equal(dvert.cpu().numpy(), want, "device vertex map")
+    assert_bits_equal(mirror.numpy(), want, "mirrored vertex map")
+    # level 2: pinned result buffers take the mirrored path, pageable ones the copy
+    outs = []
+    for pinned in (True, False):
+        hv = torch.empty((h * w, 3), dtype=torch.float32)
+        hn = torch.empty((h * w, 3), dtype=torch.float32)
+        if pinned:
+            hv, hn = hv.pin_memory(), hn.pin_memory()
+        check(lib.tsdf_b200_volume_raycast(vol._h, w, h, fptr(colmajor(cam.pose)), fptr(colmajor(cam.kinv)), hv.numpy().ctypes.data,
+                                           hn.numpy().ctypes.data))
+        outs.append((hv.numpy().copy(), hn.numpy().copy()))
+    assert_bits_equal(outs[0][0].reshape(-1), want, "level-2 vertices, pinned buffer")
+    assert_bits_equal(outs[1][0].reshape(-1), want, "level-2 vertices, pageable buffer")
+    assert_bits_equal(outs[0][1], outs[1][1], "level-2 normals")
+    assert int((~np.isnan(want.reshape(-1, 3)[:, 0])).sum()) > 5000
+    vol.close()

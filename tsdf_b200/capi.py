@@ -38,6 +38,8 @@ SIGNATURES = {
                                     _vp, _vp, _vp, _vp, _vp, _vp]),
     "tsdf_b200_raycast_ex": (C.c_int, [_vp, _u32, _u32, _u32, _f, _f, _f, C.c_float, _f, _f, _f, _u32, _u32,
                                        _vp, _vp, _vp, _vp, _vp, C.c_int, _vp]),
+    "tsdf_b200_raycast_mirrored": (C.c_int, [_vp, _u32, _u32, _u32, _f, _f, _f, C.c_float, _f, _f, _f, _u32, _u32, _vp, _vp,
+                                             _vp, _vp, _vp, C.c_int, _vp]),
     "tsdf_b200_raycast_slab": (C.c_int, [_vp, _u32, _u32, _u32, _u32, _u32, _u32, _u32, _f, _f, _f, C.c_float, _f, _f, _f,
                                          _u32, _u32, _vp, _vp, _vp, _vp, C.c_int, _vp]),
     "tsdf_b200_raycast_interleaved": (C.c_int, [_vp, _u32, _u32, _u32, _u32, _u32, _u32, _f, _f, _f, C.c_float, _f, _f, _f,

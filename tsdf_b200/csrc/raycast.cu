@@ -56,6 +56,9 @@ struct RayParams {
     uint32_t tile_first, tile_stride;
     uint32_t n_out;
     float *out[TSDF_B200_MAX_PEERS];
+    // Second copy of the vertex map in memory that is slow to write in small pieces (pinned host memory seen through the
+    // bus): each warp writes its 8x4 tile as 24 aligned 16-byte stores.  Needs width % 8 == 0, height % 4 == 0, base % 16 == 0.
+    float *mirror;
 };
 
 template <bool FASTDIV>
@@ -521,6 +524,7 @@ template <bool FASTDIV, bool SKIP, bool SLAB>
 __global__ void __launch_bounds__(128, TSDF_RAY_MINB)
 raycast_kernel(const __grid_constant__ RayParams P) {
     __shared__ float s_t[TSDF_B200_RAY_TABLE_LEN];
+    __shared__ __align__(16) float s_tile[4][96];
     for (int i = threadIdx.x; i < TSDF_B200_RAY_TABLE_LEN; i += blockDim.x) s_t[i] = P.table[i];
     __syncthreads();
 
@@ -552,10 +556,10 @@ raycast_kernel(const __grid_constant__ RayParams P) {
     }
     const uint32_t imx = (tile % tiles_x) * 8 + (lane & 7);
     const uint32_t imy = (tile / tiles_x) * 4 + (lane >> 3);
+    float ip[3] = { CUDART_NAN_F, CUDART_NAN_F, CUDART_NAN_F };
     if (imx < P.width && imy < P.height) {
         const size_t pix = (size_t)imy * P.width + imx;
         const RaySetup R = ray_setup(P, imx, imy);
-        float ip[3] = { CUDART_NAN_F, CUDART_NAN_F, CUDART_NAN_F };
         int kh = -1, dbg_iters = 0;
         float s_hit = 0.0f;
         bool queued = false;
@@ -610,6 +614,19 @@ raycast_kernel(const __grid_constant__ RayParams P) {
         }
     }
     __syncwarp();
+    if (!SLAB && P.mirror) {
+        // the tile as 4 rows of 24 floats; pixels handed to continue_kernel hold NaN here and are rewritten by it
+        float *st = s_tile[threadIdx.x >> 5];
+        st[3 * lane + 0] = ip[0]; st[3 * lane + 1] = ip[1]; st[3 * lane + 2] = ip[2];
+        __syncwarp();
+        if (lane < 24) {
+            const uint32_t row = lane / 6, q = lane % 6;
+            const float4 v = *reinterpret_cast<const float4 *>(st + 24 * row + 4 * q);
+            const size_t first = (size_t)((tile / tiles_x) * 4 + row) * P.width + (tile % tiles_x) * 8;
+            *reinterpret_cast<float4 *>(P.mirror + 3 * first + 4 * q) = v;
+        }
+        __syncwarp();
+    }
     }
 
     if (P.n_samples) {
@@ -677,6 +694,7 @@ continue_kernel(const __grid_constant__ RayParams P) {
                     P.vertices[3 * pix + 1] = ip[1];
                     P.vertices[3 * pix + 2] = ip[2];
                     if (P.khit && !P.debug_iters) P.khit[pix] = k_hit;
+                    if (P.mirror) { P.mirror[3 * pix + 0] = ip[0]; P.mirror[3 * pix + 1] = ip[1]; P.mirror[3 * pix + 2] = ip[2]; }
                 }
             }
         }
@@ -822,7 +840,7 @@ static int fill_params(RayParams &P, const float *d_dist, uint32_t nx, uint32_t 
     P.cyc_s = 0; P.cyc_g = 0; P.cyc_r = 0;
     P.vertices = nullptr; P.khit = nullptr; P.keys = nullptr; P.n_samples = nullptr; P.tile_counter = nullptr;
     P.debug_iters = getenv("TSDF_B200_DEBUG_ITERS") ? atoi(getenv("TSDF_B200_DEBUG_ITERS")) : 0;
-    P.tile_first = 0; P.tile_stride = 1; P.n_out = 0;
+    P.tile_first = 0; P.tile_stride = 1; P.n_out = 0; P.mirror = nullptr;
     P.queue = nullptr; P.queue_count = nullptr; P.queue_cap = 0;
     static const int cap = getenv("TSDF_B200_RAY_CAP") ? atoi(getenv("TSDF_B200_RAY_CAP")) : 96;
     P.max_iters = cap > 0 ? cap : 0x7fffffff;
@@ -902,6 +920,24 @@ extern "C" int tsdf_b200_raycast_ex(const float *d_dist, uint32_t nx, uint32_t n
     const BrickDims nb = brick_dims(nx, ny, nz);
     P.nbx = nb.bx; P.nby = nb.by; P.nbz = nb.bz;
     P.vertices = d_vertices; P.khit = d_khit; P.n_samples = d_n_samples;
+    return launch_march<false>(P, fastdiv, (cudaStream_t)stream);
+}
+
+extern "C" int tsdf_b200_raycast_mirrored(const float *d_dist, uint32_t nx, uint32_t ny, uint32_t nz,
+                                          const float voxel[3], const float space_min[3], const float space_max[3],
+                                          float trunc, const float origin[3], const float rot[9], const float kinv[9],
+                                          uint32_t width, uint32_t height, const float *d_table,
+                                          const uint8_t *d_occ, float *d_vertices, float *mirror,
+                                          unsigned long long *d_n_samples, int fastdiv, void *stream) {
+    if (!d_dist || !d_vertices) return TSDF_B200_EINVAL;
+    if (mirror && (width % 8 != 0 || height % 4 != 0 || ((uintptr_t)mirror & 15u) != 0)) return TSDF_B200_EINVAL;
+    RayParams P;
+    int rc = fill_params(P, d_dist, nx, ny, nz, voxel, space_min, space_max, trunc, origin, rot, kinv, width, height, d_table, &fastdiv);
+    if (rc) return rc;
+    P.occ = d_occ;
+    const BrickDims nb = brick_dims(nx, ny, nz);
+    P.nbx = nb.bx; P.nby = nb.by; P.nbz = nb.bz;
+    P.vertices = d_vertices; P.n_samples = d_n_samples; P.mirror = mirror;
     return launch_march<false>(P, fastdiv, (cudaStream_t)stream);
 }
 

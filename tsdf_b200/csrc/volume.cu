@@ -239,13 +239,23 @@ extern "C" int tsdf_b200_volume_raycast(const tsdf_b200_volume *cv, uint32_t wid
     float smin[3], smax[3];
     for (int i = 0; i < 3; i++) { smin[i] = v->off[i]; smax[i] = v->off[i] + v->phys[i]; }
     if (v->counting) TSDF_CUDA_TRY(cudaMemsetAsync(v->d_counters + 1, 0, sizeof(unsigned long long), v->stream));
-    int rc = tsdf_b200_raycast_ex(v->d_dist, v->nx, v->ny, v->nz, v->vs, smin, smax, v->trunc, origin, rot, kinv, width, height,
-                                  v->d_table, v->skipping ? v->d_occ : nullptr, d_vert, nullptr,
-                                  v->counting ? v->d_counters + 1 : nullptr, v->fastdiv, v->stream);
+    // A pinned result buffer that the device can address receives the vertex map while the march runs (the transfer then
+    // overlaps the kernel instead of following it); any other buffer gets a copy afterwards.
+    float *mirror = nullptr;
+    cudaPointerAttributes attr;
+    if (width % 8 == 0 && height % 4 == 0 && cudaPointerGetAttributes(&attr, host_vertices) == cudaSuccess &&
+        attr.type == cudaMemoryTypeHost && attr.devicePointer && ((uintptr_t)attr.devicePointer & 15u) == 0)
+        mirror = static_cast<float *>(attr.devicePointer);
+    else
+        cudaGetLastError();          // an unregistered pointer is not an error of this call
+    int rc = tsdf_b200_raycast_mirrored(v->d_dist, v->nx, v->ny, v->nz, v->vs, smin, smax, v->trunc, origin, rot, kinv, width, height,
+                                        v->d_table, v->skipping ? v->d_occ : nullptr, d_vert, mirror,
+                                        v->counting ? v->d_counters + 1 : nullptr, v->fastdiv, v->stream);
     if (rc) return rc;
     rc = tsdf_b200_normals(width, height, d_vert, d_norm, v->stream);
     if (rc) return rc;
-    TSDF_CUDA_TRY(cudaMemcpyAsync(host_vertices, d_vert, npix * 3 * sizeof(float), cudaMemcpyDeviceToHost, v->stream));
+    if (!mirror)
+        TSDF_CUDA_TRY(cudaMemcpyAsync(host_vertices, d_vert, npix * 3 * sizeof(float), cudaMemcpyDeviceToHost, v->stream));
     TSDF_CUDA_TRY(cudaMemcpyAsync(host_normals, d_norm, npix * 3 * sizeof(float), cudaMemcpyDeviceToHost, v->stream));
     if (v->counting)
         TSDF_CUDA_TRY(cudaMemcpyAsync(&v->h_counters[1], v->d_counters + 1, sizeof(unsigned long long), cudaMemcpyDeviceToHost, v->stream));

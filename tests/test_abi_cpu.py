@@ -60,3 +60,34 @@ def test_product_does_not_import_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".cpp", ".hpp", ".h")):
                 src = open(os.path.join(dirpath, f), errors="ignore").read()
                 assert "oracle" not in src.replace("CPU oracle", "").lower() or f == "scenes.py", (dirpath, f)
+
+
+def test_exchange_entry_points_validate_arguments(built):
+    """The multi-GPU exchange calls reject bad arguments before any CUDA call (no device here)."""
+    import ctypes as C
+    from tsdf_b200 import capi
+    lib = capi.lib
+    one = (C.c_void_p * 1)(C.c_void_p(16))
+    none = (C.c_void_p * 1)(None)
+    # bricks_push: null source / zero destinations / too many / slab not a multiple of the brick / rank >= world / null dst
+    assert lib.tsdf_b200_bricks_push(None, 8, 8, 8, 8, 1, 0, C.c_void_p(16), 1, one, None, None) == -1
+    assert lib.tsdf_b200_bricks_push(C.c_void_p(16), 8, 8, 8, 8, 1, 0, C.c_void_p(16), 0, one, None, None) == -1
+    assert lib.tsdf_b200_bricks_push(C.c_void_p(16), 8, 8, 8, 8, 1, 0, C.c_void_p(16), 17, one, None, None) == -1
+    assert lib.tsdf_b200_bricks_push(C.c_void_p(16), 8, 8, 8, 12, 1, 0, C.c_void_p(16), 1, one, None, None) == -1
+    assert lib.tsdf_b200_bricks_push(C.c_void_p(16), 8, 8, 8, 8, 2, 2, C.c_void_p(16), 1, one, None, None) == -1
+    assert lib.tsdf_b200_bricks_push(C.c_void_p(16), 8, 8, 8, 8, 1, 0, C.c_void_p(16), 1, none, None, None) == -1
+    f3 = capi.fptr(np.ones(3, np.float32))
+    f9 = capi.fptr(np.eye(3, dtype=np.float32).reshape(-1))
+    # raycast_tiles: rank >= world, no outputs; raycast_mirrored: image not a whole number of 8x4 tiles, misaligned mirror
+    assert lib.tsdf_b200_raycast_tiles(C.c_void_p(16), 8, 8, 8, f3, f3, f3, 1.0, f3, f9, f9, 8, 4, C.c_void_p(16), None,
+                                       2, 2, 1, one, None, 0, None) == -1
+    assert lib.tsdf_b200_raycast_tiles(C.c_void_p(16), 8, 8, 8, f3, f3, f3, 1.0, f3, f9, f9, 8, 4, C.c_void_p(16), None,
+                                       1, 0, 0, one, None, 0, None) == -1
+    assert lib.tsdf_b200_raycast_mirrored(C.c_void_p(16), 8, 8, 8, f3, f3, f3, 1.0, f3, f9, f9, 10, 4, C.c_void_p(16), None,
+                                          C.c_void_p(16), C.c_void_p(32), None, 0, None) == -1
+    assert lib.tsdf_b200_raycast_mirrored(C.c_void_p(16), 8, 8, 8, f3, f3, f3, 1.0, f3, f9, f9, 8, 4, C.c_void_p(16), None,
+                                          C.c_void_p(16), C.c_void_p(36), None, 0, None) == -1
+    p = C.c_void_p()
+    assert lib.tsdf_b200_peer_open(None, C.byref(p)) == -1
+    assert lib.tsdf_b200_peer_alloc(0, C.byref(p), None) == -1
+    assert lib.tsdf_b200_peer_close(None) == 0 and lib.tsdf_b200_peer_free(None) == 0

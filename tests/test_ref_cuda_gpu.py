@@ -138,3 +138,46 @@ def test_reference_cuda_random_poses_sphere(R):
     assert_bits_equal(dm, dr, "tsdf_b200 dist vs reference CUDA")
     assert_bits_equal(wm, wr, "tsdf_b200 weight vs reference CUDA")
     rv.close(); mv.close()
+
+
+def test_reference_cuda_timing_at_256(R):
+    """SURVEY.md section 8d, "also time": the reference's own CUDA path (its classes and kernels, rebuilt -O3 for sm_100,
+    host buffers, per-call allocations as shipped) next to tsdf_b200's level-2 calls on the same frames, 256^3 (BASELINE
+    configs[1]).  The volumes must agree bit for bit; the times go to gpurun_out/ref_cuda_timing.json for DESIGN.md."""
+    import time
+    import torch
+    from tsdf_b200 import Volume, scenes
+    lib = R.RefLib("O3")
+    n, phys, w, h = (256, 256, 256), (3000.0, 3000.0, 3000.0), 640, 480
+    rv = R.RefVolume(lib, n, phys)
+    mv = Volume(n, phys)
+    frames = [scenes.orbit_camera(f, 1000) for f in range(6)]
+    depths = [scenes.render_depth(c, w, h) for c in frames]
+    mats = [lib.camera_matrices(c.k, c.pose) for c in frames]
+    t = {"ref_integrate_ms": [], "ref_raycast_ms": [], "b200_integrate_ms": [], "b200_raycast_ms": []}
+    Vbuf, Nbuf = np.zeros((h * w, 3), np.float32), np.zeros((h * w, 3), np.float32)
+    for i, cam in enumerate(frames):
+        kinv, inv_pose = mats[i]
+        torch.cuda.synchronize()
+        t0 = time.perf_counter(); rv.integrate(depths[i], cam.k, cam.pose); torch.cuda.synchronize(); t1 = time.perf_counter()
+        Vr, Nr = rv.raycast(w, h, cam.k, cam.pose); torch.cuda.synchronize(); t2 = time.perf_counter()
+        mv.integrate(depths[i], inv_pose, cam.k, kinv); torch.cuda.synchronize(); t3 = time.perf_counter()
+        Vm, Nm = mv.raycast(w, h, cam.pose, kinv, Vbuf, Nbuf); torch.cuda.synchronize(); t4 = time.perf_counter()
+        if i >= 2:                      # first calls: lazy kernel loading, self-test, allocations
+            t["ref_integrate_ms"].append((t1 - t0) * 1e3); t["ref_raycast_ms"].append((t2 - t1) * 1e3)
+            t["b200_integrate_ms"].append((t3 - t2) * 1e3); t["b200_raycast_ms"].append((t4 - t3) * 1e3)
+    assert_bits_equal(Vm, Vr, "vertices, tsdf_b200 vs reference CUDA at 256^3")
+    assert_bits_equal(Nm, Nr, "normals, tsdf_b200 vs reference CUDA at 256^3")
+    dr, wr = rv.read()
+    dm, wm = mv.read()
+    assert_bits_equal(dm, dr, "dist at 256^3")
+    assert_bits_equal(wm, wr, "weight at 256^3")
+    out = {k: float(np.median(v)) for k, v in t.items()}
+    out["config"] = "256^3 / 3000 mm, 640x480, orbit frames 2..5, host buffers (pageable), synchronous calls"
+    out["ref_frames_per_s"] = 1e3 / (out["ref_integrate_ms"] + out["ref_raycast_ms"])
+    out["b200_frames_per_s"] = 1e3 / (out["b200_integrate_ms"] + out["b200_raycast_ms"])
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    if os.path.isdir(os.path.join(root, "gpurun_out")):
+        json.dump(out, open(os.path.join(root, "gpurun_out", "ref_cuda_timing.json"), "w"))
+    assert out["b200_frames_per_s"] > out["ref_frames_per_s"]
+    rv.close(); mv.close()

@@ -181,9 +181,11 @@ int tsdf_b200_raycast_interleaved(const float *d_dist_local, uint32_t nx, uint32
  * tsdf_b200_raycast_tiles, barrier, tsdf_b200_normals.
  *
  * tsdf_b200_bricks_push: copies every owned brick that has a flagged brick in its 27-neighbourhood (d_occ_global, merged
- * flags) from this rank's slabs into the n_dst replicas d_dst[0..n_dst) (host array of device pointers; peers' replicas
- * are written through NVLink).  That set covers every voxel a ray can read: a sample is evaluated only inside a flagged
- * brick b and reads voxels of [8b-1, 8b+8]^3.  d_n_bricks (optional) += bricks copied.                                  */
+ * flags), and every owned brick on a low face of the volume (bx, by or bz == 0), from this rank's slabs into the n_dst
+ * replicas d_dst[0..n_dst) (host array of device pointers; peers' replicas are written through NVLink).  That set covers
+ * every voxel a ray can read: away from the low faces a sample is evaluated only inside a flagged brick b and reads voxels
+ * of [8b-1, 8b+8]^3; voxel layer 0 of each axis is always evaluated (the reference extrapolates there) and reads layers 0
+ * and 1.  d_n_bricks (optional) += bricks copied.                                                                      */
 int tsdf_b200_bricks_push(const float *d_dist_local, uint32_t nx, uint32_t ny, uint32_t nz,
                           uint32_t slab_planes, uint32_t world, uint32_t rank,
                           const uint8_t *d_occ_global, uint32_t n_dst, float *const *d_dst,
@@ -267,11 +269,15 @@ void tsdf_b200_volume_destroy(tsdf_b200_volume *v);
 
 int tsdf_b200_volume_get(const tsdf_b200_volume *v, uint32_t size[3], float physical[3],
                          float voxel[3], float offset[3], float *trunc, float *max_weight);
+/* global_translation() / global_rotation() (include/TSDFVolume.hpp:216,223): zero unless the volume was loaded from a
+ * .tsdf file whose header carries them (TSDF/TSDFVolume.cu:496-497). */
+int tsdf_b200_volume_get_global(const tsdf_b200_volume *v, float translation[3], float rotation[3]);
 /* TSDFVolume::offset(ox,oy,oz) (include/TSDFVolume.hpp:144-148). */
 int tsdf_b200_volume_set_offset(tsdf_b200_volume *v, float ox, float oy, float oz);
 /* TSDFVolume::clear (TSDF/TSDFVolume.cu:812-845). */
 int tsdf_b200_volume_clear(tsdf_b200_volume *v);
-/* distance_data()/weight_data(): raw device pointers, valid on the default stream. */
+/* distance_data()/weight_data(): raw device pointers.  The volume works on a blocking stream of its own, so kernels and
+ * copies a caller issues on the legacy default stream are ordered against the volume's calls in both directions. */
 const float *tsdf_b200_volume_distance_data(const tsdf_b200_volume *v);
 const float *tsdf_b200_volume_weight_data(const tsdf_b200_volume *v);
 /* deformation(): materialises the 24 B/voxel node array on first use. */

@@ -14,7 +14,10 @@
 # HOST side of the .cu files is compiled at -O0: GPURaycaster.cu:455 keeps camera.kinv().data() of a temporary
 # and reads it on :456-460 — harmless with in-object matrix storage at -O0, clobbered stack when the host
 # compiler optimises (every ray then misses).  Device code is optimised regardless of the host -O level.  libpng is absent: the PNG function and the DepthImage
-# constructor the linked files reference are stubbed in oracle/ref_harness.cu (never called on this path).
+# constructor/accessors the linked files reference are stubbed in oracle/ref_harness.cu (the PNG stub keeps the depth
+# map render_to_depth_image hands it, which is how the tests read that function's result).
+# MarchingCubes/MarkAndSweepMC.cu (which #includes the two MC_*_table.cu files) compiles unmodified: it pins the
+# marching-cubes oracle (extract_surface, :506-555).
 # TEST INFRASTRUCTURE ONLY.
 set -e
 HERE="$(cd "$(dirname "$0")" && pwd)"
@@ -33,7 +36,8 @@ INC="-I$HERE/../tsdf_b200/compat -I$REF/include -I$REF"
 sed 's/success = ifs\.read/success = (bool)ifs.read/' "$REF/TSDF/TSDFVolume.cu" | \
     sed 's#"\.\./include/#"'"$REF"'/include/#' > "$OUT/build/TSDFVolume_patched.cu"
 SRCS="$OUT/build/TSDFVolume_patched.cu $REF/TSDF/TSDF_utilities.cu $REF/Utilities/cuda_coordinate_transforms.cu \
-      $REF/Utilities/cuda_utilities.cu $REF/RayCaster/GPURaycaster.cu $HERE/ref_harness.cu"
+      $REF/Utilities/cuda_utilities.cu $REF/RayCaster/GPURaycaster.cu $REF/MarchingCubes/MarkAndSweepMC.cu \
+      $HERE/ref_harness.cu"
 HOST="$REF/Camera.cpp $REF/Utilities/Definitions.cpp"
 build() {   # $1 = tag, rest = flags
     tag=$1; shift

@@ -1,7 +1,9 @@
 """ctypes wrapper of oracle/_ref/libref_cuda_{O3,G}.so — the REFERENCE's own CUDA kernels and host classes,
 compiled from /root/reference/src by oracle/build_ref.sh.  TEST INFRASTRUCTURE ONLY (GPU box)."""
+import contextlib
 import ctypes as C
 import os
+import sys
 
 import numpy as np
 
@@ -9,6 +11,22 @@ _DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")
 _f = C.POINTER(C.c_float)
 _vp = C.c_void_p
 _u32 = C.c_uint32
+
+
+@contextlib.contextmanager
+def quiet():
+    """fd 1 -> /dev/null while the reference runs: its host code prints per call (std::cout) and process_ray prints one
+    line per ray that reaches the 4402-sample cap (GPURaycaster.cu:370) — hundreds of thousands of lines at 512^3."""
+    sys.stdout.flush()
+    saved = os.dup(1)
+    null = os.open(os.devnull, os.O_WRONLY)
+    try:
+        os.dup2(null, 1)
+        yield
+    finally:
+        os.dup2(saved, 1)
+        os.close(null)
+        os.close(saved)
 
 
 def available(tag="O3"):
@@ -43,6 +61,15 @@ class RefLib:
         lib.ref_volume_save.argtypes = [_vp, C.c_char_p]
         lib.ref_volume_load.restype = _vp
         lib.ref_volume_load.argtypes = [C.c_char_p]
+        lib.ref_volume_set_weight_data.argtypes = [_vp, _vp]
+        lib.ref_volume_distance_ptr.restype = _vp
+        lib.ref_volume_distance_ptr.argtypes = [_vp]
+        lib.ref_volume_weight_ptr.restype = _vp
+        lib.ref_volume_weight_ptr.argtypes = [_vp]
+        lib.ref_render_depth.argtypes = [_vp, _u32, _u32, _f, _f, _vp]
+        lib.ref_extract_surface.restype = C.c_longlong
+        lib.ref_extract_surface.argtypes = [_vp, C.POINTER(_vp)]
+        lib.ref_free.argtypes = [_vp]
 
     def camera_matrices(self, k, pose):
         """(kinv 3x3, inv_pose 4x4) exactly as the reference Camera derives them."""
@@ -100,6 +127,34 @@ class RefVolume:
     def set_distance_data(self, d):
         d = np.ascontiguousarray(d, np.float32)
         self.r.lib.ref_volume_set_distance_data(self.h, d.ctypes.data)
+
+    @property
+    def distance_ptr(self):
+        return self.r.lib.ref_volume_distance_ptr(self.h)
+
+    @property
+    def weight_ptr(self):
+        return self.r.lib.ref_volume_weight_ptr(self.h)
+
+    def set_weight_data(self, w):
+        w = np.ascontiguousarray(w, np.float32)
+        self.r.lib.ref_volume_set_weight_data(self.h, w.ctypes.data)
+
+    def render_depth(self, w, h, k, pose):
+        """GPURaycaster(w, h).render_to_depth_image(volume, camera) -> (h, w) uint16."""
+        out = np.empty((h, w), np.uint16)
+        assert self.r.lib.ref_render_depth(self.h, w, h, _fp(_cm(k)), _fp(_cm(pose)), out.ctypes.data) == 0
+        return out
+
+    def extract_surface(self):
+        """extract_surface(volume, vertices, triangles) -> (n, 3) float32 vertices (triangle i = vertices 3i, 3i+2, 3i+1,
+        checked inside the harness).  The reference exit()s on an empty surface: only call with a surface present."""
+        p = _vp()
+        n = self.r.lib.ref_extract_surface(self.h, C.byref(p))
+        assert n >= 0, "reference triangle list is not (i, i+2, i+1)"
+        v = np.ctypeslib.as_array(C.cast(p, _f), shape=(max(n, 1) * 3,))[: n * 3].copy().reshape(-1, 3)
+        self.r.lib.ref_free(p)
+        return v
 
     def save(self, path):
         assert self.r.lib.ref_volume_save(self.h, os.fsencode(path)) == 0

@@ -323,9 +323,36 @@ static void gpu_tests() {
     CHECK(hits == 0);
 }
 
+// --render-depth <dir> <n> <physical> <w> <h>: GPURaycaster(w, h).render_to_depth_image of an n^3 volume whose distances
+// come from <dir>/dist.f32, seen by Camera(K) with set_pose(pose) from <dir>/camera.f32 (9 + 16 floats, column-major);
+// writes <dir>/depth.u16.  tests/test_ref_cuda_gpu.py compares it with the reference's own function (oracle/_ref).
+static int render_depth_mode(const std::string &dir, int n, float physical, int w, int h) {
+    std::vector<float> dist(static_cast<size_t>(n) * n * n), cam(25);
+    std::ifstream fd(dir + "/dist.f32", std::ios::binary), fc(dir + "/camera.f32", std::ios::binary);
+    if (!fd.read(reinterpret_cast<char *>(dist.data()), dist.size() * sizeof(float))) return 2;
+    if (!fc.read(reinterpret_cast<char *>(cam.data()), cam.size() * sizeof(float))) return 2;
+    TSDFVolume volume(TSDFVolume::UInt3{static_cast<uint32_t>(n), static_cast<uint32_t>(n), static_cast<uint32_t>(n)},
+                      TSDFVolume::Float3{physical, physical, physical});
+    volume.set_distance_data(dist.data());
+    Eigen::Matrix3f k;
+    std::memcpy(k.data(), cam.data(), 9 * sizeof(float));
+    Camera camera(k);
+    Matrix4f pose;
+    std::memcpy(pose.data(), cam.data() + 9, 16 * sizeof(float));
+    camera.set_pose(pose);
+    GPURaycaster raycaster(w, h);
+    std::unique_ptr<DepthImage> image(raycaster.render_to_depth_image(volume, camera));
+    if (!image || image->width() != w || image->height() != h) return 3;
+    std::ofstream out(dir + "/depth.u16", std::ios::binary);
+    out.write(reinterpret_cast<const char *>(image->data()), static_cast<size_t>(w) * h * sizeof(uint16_t));
+    return out ? 0 : 4;
+}
+
 int main(int argc, char **argv) {
     bool gpu = false;
     g_tmp = "/tmp";
+    if (argc == 7 && std::string(argv[1]) == "--render-depth")
+        return render_depth_mode(argv[2], std::atoi(argv[3]), static_cast<float>(std::atof(argv[4])), std::atoi(argv[5]), std::atoi(argv[6]));
     for (int i = 1; i < argc; i++) {
         if (std::string(argv[i]) == "--gpu") gpu = true;
         else g_tmp = argv[i];

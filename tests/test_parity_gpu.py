@@ -605,13 +605,103 @@ def test_replica_image_sharding_equals_whole(G, world, slab, n):
             e.finish(320, 240)
         torch.cuda.synchronize()
         flagged = int(merged.sum().item())
-        assert flagged <= pushed <= 27 * flagged and pushed <= merged.numel()
+        nb = [(x + 7) // 8 for x in n]
+        low_face = nb[0] * nb[1] * nb[2] - (nb[0] - 1) * (nb[1] - 1) * (nb[2] - 1)      # always pushed (low-edge layer)
+        assert flagged <= pushed <= 27 * flagged + low_face and pushed <= merged.numel()
         for e in ranks:
             assert_bits_equal(e.vertices.cpu().numpy(), whole.vertices.cpu().numpy(), f"vertices of rank {e.rank}, frame {frame}")
             assert_bits_equal(e.normals.cpu().numpy(), whole.normals.cpu().numpy(), f"normals of rank {e.rank}, frame {frame}")
     assert int((~torch.isnan(whole.vertices.view(-1, 3)[:, 0])).sum()) > 5000
     # the merged flags equal the single volume's flags: nothing a rank cannot see decides a brick
     assert torch.equal(merged, whole.occ[:merged.numel()])
+    for e in ranks:
+        e.close()
+    whole.close()
+
+
+def _load_engine_planes(e, planes, n, slab):
+    """Writes a whole-volume distance array (nz, ny*nx) into a replica-layout engine's slabs (+ halo planes)."""
+    ld = e.dist.view(-1, n[0] * n[1])
+    for j, (z0, z1) in enumerate(e.slabs):
+        stored = (z1 - z0) + (1 if z1 < n[2] else 0)
+        ld[j * (slab + 1): j * (slab + 1) + stored].copy_(planes[z0:z0 + stored])
+
+
+def test_replica_low_face_extrapolation_and_clear(G):
+    """Advisor findings (round 1) on layout="replica".  (1) Voxel layer 0 of each axis is always evaluated and
+    EXTRAPOLATED by the reference (u in [-0.5, 0)): two positive-band corners c0 = 0.2*trunc, c1 = trunc give a sample <= 0,
+    i.e. a hit, inside a brick that is not flagged — the push must publish low-face bricks regardless of flags (replicas
+    are NaN-poisoned here, so a brick that was not pushed shows).  (2) clear() must reset the replica: after a clear the
+    bricks pushed earlier are no longer flagged nor pushed, but the low-edge layer of them is still read."""
+    import ctypes as C
+    import torch
+    from tsdf_b200 import scenes, sharded
+    from tsdf_b200.capi import lib, check
+    world, slab, n, phys = 2, 16, (64, 64, 64), (3000.0, 3000.0, 3000.0)
+    w, h = 320, 240
+    whole = sharded.ShardedEngine(n, phys)
+    ranks = [sharded.ShardedEngine(n, phys, rank=r, world=world, layout="replica", slab=slab) for r in range(world)]
+    for e in ranks:
+        check(lib.tsdf_b200_fill_f32(C.c_void_p(e.replica), n[0] * n[1] * n[2], float("nan"), e.stream))
+        e.connect(w, h, peers=ranks)
+    t = float(whole.trunc)
+    vol = torch.full((n[2], n[1], n[0]), t, dtype=torch.float32, device="cuda")
+    vol[:, :, 0] = 0.2 * t            # x layer 0: extrapolates to <= 0 within the first quarter voxel
+    vol[:, 0, 8:40] = 0.3 * t         # part of y layer 0
+    vol[0, 20:50, :] = 0.25 * t       # part of z layer 0
+    planes = vol.view(n[2], -1)
+    whole.dist.copy_(vol.view(-1))
+    check(lib.tsdf_b200_occupancy_rebuild(C.c_void_p(whole.dist.data_ptr()), *n, whole.trunc, C.c_void_p(whole.occ.data_ptr()), whole.stream))
+    for e in ranks:
+        _load_engine_planes(e, planes, n, slab)
+    nbricks = 8 * 8 * 8
+    assert int(whole.occ[:nbricks].sum().item()) == 0          # every voxel is in the positive band: nothing is flagged
+
+    def run(cam):
+        whole.raycast(w, h, cam)
+        for e in ranks:
+            e.push()
+        torch.cuda.synchronize()
+        for e in ranks:
+            e.march_tiles(w, h, cam)
+        for e in ranks:
+            e.finish(w, h)
+        torch.cuda.synchronize()
+        for e in ranks:
+            assert_bits_equal(e.vertices.cpu().numpy(), whole.vertices.cpu().numpy(), f"vertices of rank {e.rank}")
+        return int((~torch.isnan(whole.vertices.view(-1, 3)[:, 0])).sum())
+
+    hits = 0
+    for pos in ((-2500.0, 1400.0, 1300.0), (1600.0, -2500.0, 1500.0), (1500.0, 1500.0, -2500.0)):
+        cam = scenes.PinholeCamera(295.5, 295.0, 165.5, 117.3)
+        cam.move_to(*pos)
+        cam.look_at(1500.0, 1500.0, 1500.0)
+        hits += run(cam)
+    assert hits > 20000                  # the extrapolated low-edge hits exist (single-GPU path == oracle elsewhere)
+
+    # (2) integrate a frame (surface bricks get flagged and pushed), clear, integrate a different view: same as the whole
+    for e in ranks:
+        e.clear()
+    whole.clear()
+    cams = [scenes.orbit_camera(i, 12) for i in (1, 7)]
+    for cam in cams:
+        k = cam.k.copy(); k[:2] *= 0.5
+        cam.k = k
+        cam.kinv = np.linalg.inv(k.astype(np.float64)).astype(np.float32)
+    for phase, cam in enumerate(cams):
+        depth = torch.from_numpy(scenes.render_depth(cam, w, h)).cuda()
+        whole.integrate(depth, cam)
+        for e in ranks:
+            e.integrate(depth, cam)
+        merged = torch.maximum(ranks[0].flags(), ranks[1].flags()).clone()
+        for e in ranks:
+            e.flags().copy_(merged)
+        assert run(cam) > 3000
+        # a different view of the pre-clear surface would hit stale voxels if the replica kept them
+        if phase == 0:
+            for e in ranks:
+                e.clear()
+            whole.clear()
     for e in ranks:
         e.close()
     whole.close()

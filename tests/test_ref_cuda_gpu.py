@@ -140,6 +140,168 @@ def test_reference_cuda_random_poses_sphere(R):
     rv.close(); mv.close()
 
 
+def test_reference_marching_cubes_equals_oracle_and_gpu(R):
+    """the reference's own extract_surface (MarchingCubes/MarkAndSweepMC.cu:506-555, compiled
+    unmodified into oracle/_ref) == the CPU oracle == tsdf_b200_mc_extract, vertex for vertex and bit for bit — on a
+    noisy sphere uploaded with set_distance_data (offset volume, anisotropic voxels) and on a volume fused from orbit
+    frames by the reference itself."""
+    import ctypes as C
+    import torch
+    from oracle import oracle
+    from tsdf_b200 import scenes
+    from tsdf_b200.capi import lib as mylib, check, fptr
+    from test_parity_gpu import sphere_sdf
+    from test_mc_gpu import gpu_mc
+    lib = R.RefLib("O3")
+    rng = np.random.default_rng(5)
+
+    def compare(rv, n, what):
+        d, _ = rv.read()
+        vox, off = rv.voxel, np.asarray(rv._offset, np.float32)
+        want = rv.extract_surface()
+        assert want.shape[0] > 1000 and want.shape[0] % 3 == 0
+        assert_bits_equal(oracle.mc_extract(d, n, vox, off), want, f"{what}: oracle vs reference marching cubes")
+        got = gpu_mc(mylib, check, fptr, torch.from_numpy(d).cuda(), n, 0, 0, n[2] - 1, vox, off)
+        assert got.shape == want.shape
+        assert_bits_equal(got, want, f"{what}: tsdf_b200_mc_extract vs reference marching cubes")
+
+    n, phys = (72, 64, 56), (2800.0, 3000.0, 2600.0)
+    rv = R.RefVolume(lib, n, phys)
+    rv.offset(100.0, -40.0, 60.0); rv._offset = (100.0, -40.0, 60.0)
+    sdf = sphere_sdf(n, phys, rv.trunc, (1400, 1500, 1300), 700)
+    sdf = (sdf + rng.normal(scale=0.02 * float(rv.trunc), size=sdf.shape)).astype(np.float32)
+    sdf[rng.integers(0, sdf.size, size=7)] = 0.0              # exact zeros count as outside (:139-146)
+    rv.set_distance_data(sdf)
+    compare(rv, n, "noisy sphere")
+    rv.close()
+
+    n, phys = (64, 64, 64), (3000.0, 3000.0, 3000.0)
+    rv = R.RefVolume(lib, n, phys); rv._offset = (0.0, 0.0, 0.0)
+    for f in (0, 3, 7):
+        cam = scenes.orbit_camera(f, 12)
+        k = scaled(cam, 0.5)
+        rv.integrate(scenes.render_depth(cam, 320, 240), k, cam.pose)
+    compare(rv, n, "fused orbit volume")
+    rv.close()
+
+
+def test_reference_render_to_depth_image_values(R, tmp_path):
+    """SURVEY.md section 8(f4): GPURaycaster::render_to_depth_image (RayCaster/GPURaycaster.cu:555-606 — raycast, then
+    (uint16_t)roundf(world_to_camera(vertex).z) per pixel, :577-581) through the drop-in class == the reference's own
+    function, pixel for pixel."""
+    import subprocess
+    from test_classes_cpu import build_class_tests
+    from test_parity_gpu import sphere_sdf
+    from tsdf_b200 import scenes
+    from tsdf_b200.capi import colmajor
+    lib = R.RefLib("O3")
+    n, phys, w, h = 64, 3000.0, 320, 240
+    rv = R.RefVolume(lib, (n,) * 3, (phys,) * 3)
+    sdf = sphere_sdf((n,) * 3, (phys,) * 3, rv.trunc, (1500, 1450, 1550), 900)
+    rv.set_distance_data(sdf)
+    exe = build_class_tests()
+    rng = np.random.default_rng(11)
+    total_hits = 0
+    for i in range(3):
+        cam = random_rigid_pose(rng, radius=(2200.0, 4200.0))
+        k = scaled(cam, 0.5)
+        want = rv.render_depth(w, h, k, cam.pose)
+        sdf.tofile(tmp_path / "dist.f32")
+        np.concatenate([colmajor(k), colmajor(cam.pose)]).astype(np.float32).tofile(tmp_path / "camera.f32")
+        out = subprocess.run([exe, "--render-depth", str(tmp_path), str(n), str(phys), str(w), str(h)], capture_output=True, text=True)
+        assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+        got = np.fromfile(tmp_path / "depth.u16", np.uint16).reshape(h, w)
+        assert np.array_equal(got, want), f"pose {i}: {(got != want).sum()} of {got.size} depth pixels differ"
+        total_hits += int((want > 0).sum())
+    assert total_hits > 20000
+    rv.close()
+
+
+class _Raw:
+    """A raw device pointer as a torch tensor (no copy): full-size volumes are compared where they live."""
+
+    def __init__(self, ptr, count, typestr="<f4"):
+        self.__cuda_array_interface__ = {"shape": (count,), "typestr": typestr, "data": (int(ptr), False), "version": 2}
+
+
+def _dev_i32(ptr, count):
+    import torch
+    return torch.as_tensor(_Raw(ptr, count, "<i4"), device="cuda")
+
+
+def _fullsize_against_reference(R, size, frames, raycast_frames, w, h, slabs=0):
+    """Integrates orbit frames into a size^3 volume with the reference's own classes (oracle/_ref, -O3 -fmad=false) and with
+    the level-2 C-ABI, compares dist / weight on the device and vertices / normals / hit voxels on the host, bit for bit."""
+    import torch
+    from oracle import oracle
+    from tsdf_b200 import Volume, scenes
+    lib = R.RefLib("O3")
+    n, phys = (size,) * 3, (3000.0,) * 3
+    nv = size ** 3
+    with R.quiet():
+        rv = R.RefVolume(lib, n, phys)
+    mv = Volume(n, phys)
+    assert rv.trunc == mv.trunc
+    V = {}
+    for f in frames:
+        cam = scenes.orbit_camera(f, 1000)
+        kinv, inv_pose = lib.camera_matrices(cam.k, cam.pose)
+        depth = scenes.render_depth(cam, w, h)
+        with R.quiet():
+            rv.integrate(depth, cam.k, cam.pose)
+        mv.integrate(depth, inv_pose, cam.k, kinv)
+        if f in raycast_frames:
+            with R.quiet():                                   # capped rays print one line each (GPURaycaster.cu:370)
+                Vr, Nr = rv.raycast(w, h, cam.k, cam.pose)
+            Vm, Nm = mv.raycast(w, h, cam.pose, kinv)
+            assert_bits_equal(Vm, Vr, f"{size}^3 frame {f}: vertices vs reference CUDA")
+            assert_bits_equal(Nm, Nr, f"{size}^3 frame {f}: normals vs reference CUDA")
+            hv = oracle.hit_voxels(Vm, np.zeros(3, np.float32), mv.voxel, size, size)
+            hr = oracle.hit_voxels(Vr, np.zeros(3, np.float32), mv.voxel, size, size)
+            assert np.array_equal(hv, hr), f"{size}^3 frame {f}: hit voxel indices"
+            V[f] = (Vr, int((~np.isnan(Vr[:, 0])).sum()), cam, kinv)
+        torch.cuda.synchronize()
+        assert torch.equal(_dev_i32(rv.distance_ptr, nv), _dev_i32(mv.distance_ptr, nv)), f"{size}^3 frame {f}: dist vs reference CUDA"
+        assert torch.equal(_dev_i32(rv.weight_ptr, nv), _dev_i32(mv.weight_ptr, nv)), f"{size}^3 frame {f}: weight vs reference CUDA"
+    assert sum(v[1] for v in V.values()) > 50000
+    if slabs:
+        # the multi-GPU raycast (Z-slabs, key min, resolve), ranks emulated on this GPU, against the reference's vertices
+        import gpu_util
+        dv = gpu_util.DeviceVolume.__new__(gpu_util.DeviceVolume)
+        dv.n, dv.physical = n, np.asarray(phys, np.float32)
+        dv.voxel, dv.trunc = mv.voxel, mv.trunc
+        dv.offset = np.zeros(3, np.float32)
+        dv.dist = torch.as_tensor(_Raw(mv.distance_ptr, nv), device="cuda")
+        dv.table = torch.empty(4416, dtype=torch.float32, device="cuda")
+        from tsdf_b200.capi import lib as mylib, check
+        import ctypes as C
+        check(mylib.tsdf_b200_ray_table(dv.trunc, C.c_void_p(dv.table.data_ptr()), None))
+        f = max(V)
+        Vr, _, cam, kinv = V[f]
+        Vs, _, _ = gpu_util.raycast_sharded_on_one_gpu(dv, w, h, cam.pose, kinv, slabs)
+        assert_bits_equal(Vs, Vr, f"{size}^3 frame {f}: {slabs}-slab raycast vs reference CUDA")
+    with R.quiet():
+        rv.close()
+    mv.close()
+
+
+def test_reference_cuda_512_headline_config(R):
+    """BASELINE configs[2] at its real size: 512^3 / 3000 mm, 640x480, orbit frames 3, 250, 500, 750 fused by the
+    reference's own CUDA path and by tsdf_b200; raycast after the first and the last of them."""
+    _fullsize_against_reference(R, 512, [3, 250, 500, 750], {3, 750}, 640, 480)
+
+
+def test_reference_cuda_1024_slabs(R):
+    """BASELINE configs[3] at its real size: 1024^3 (8 GiB of dist + weight here, 35 GiB in the reference with its
+    deformation and colour arrays): two orbit frames, single-GPU raycast and the 8-slab sharded raycast (ranks emulated)
+    against the reference's vertices."""
+    import torch
+    free, _ = torch.cuda.mem_get_info()
+    if free < 60 * 2 ** 30:
+        pytest.skip("needs ~50 GiB of free device memory")
+    _fullsize_against_reference(R, 1024, [3, 130], {130}, 640, 480, slabs=8)
+
+
 def test_reference_cuda_timing_at_256(R):
     """SURVEY.md section 8d, "also time": the reference's own CUDA path (its classes and kernels, rebuilt -O3 for sm_100,
     host buffers, per-call allocations as shipped) next to tsdf_b200's level-2 calls on the same frames, 256^3 (BASELINE

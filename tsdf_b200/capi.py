@@ -65,6 +65,7 @@ SIGNATURES = {
     "tsdf_b200_volume_load": (C.c_int, [C.c_char_p, C.POINTER(_vp)]),
     "tsdf_b200_volume_destroy": (None, [_vp]),
     "tsdf_b200_volume_get": (C.c_int, [_vp, C.POINTER(_u32), _f, _f, _f, _f, _f]),
+    "tsdf_b200_volume_get_global": (C.c_int, [_vp, _f, _f]),
     "tsdf_b200_volume_set_offset": (C.c_int, [_vp, C.c_float, C.c_float, C.c_float]),
     "tsdf_b200_volume_clear": (C.c_int, [_vp]),
     "tsdf_b200_volume_distance_data": (_vp, [_vp]),

@@ -8,9 +8,13 @@
 // against its own copy with the single-GPU kernel — bit-identical samples, balanced work whatever slab the surface
 // happens to lie in.
 //
-// What a ray can read (raycast.cu): a sample whose voxel lies in brick b is evaluated only when b is flagged, and it
-// then reads voxels of [8b-1, 8b+8]^3.  Hence the set to publish is every brick with a flagged brick in its 27-
-// neighbourhood; everything else in a replica may be stale or never written.
+// What a ray can read (raycast.cu): away from the low faces of the volume a sample whose voxel lies in brick b is
+// evaluated only when b is flagged, and it then reads voxels of [8b-1, 8b+8]^3: every brick with a flagged brick in its
+// 27-neighbourhood is published.  Voxel layer 0 of each axis is the exception — the march never skips it, flagged or not,
+// because the reference extrapolates there (u in [-0.5, 0), raycast.cu "off_low_edge") and an extrapolated sample of two
+// positive corners can be <= 0 — and its samples read voxel layers 0 and 1 of that axis: every brick on a low face
+// (bx == 0, by == 0 or bz == 0) is therefore published every frame as well.  Everything else in a replica may be stale
+// or never written.
 #include "common.cuh"
 #include <string.h>
 
@@ -35,8 +39,8 @@ bricks_push_kernel(const __grid_constant__ PushParams P) {
     const uint32_t j = blockIdx.y / layers_per_slab, lb = blockIdx.y % layers_per_slab;    // owned slab, layer inside it
     const uint32_t bz = (j * P.world + P.rank) * layers_per_slab + lb;                      // global brick layer
     if (bz >= P.nbz) return;
-    int wanted = 0;
-    if (threadIdx.x < 27) {
+    int wanted = (bx == 0u || by == 0u || bz == 0u) ? 1 : 0;          // low-face bricks: always read by the march
+    if (!wanted && threadIdx.x < 27) {
         const int cx = (int)bx + (int)(threadIdx.x % 3) - 1, cy = (int)by + (int)(threadIdx.x / 3 % 3) - 1,
                   cz = (int)bz + (int)(threadIdx.x / 9) - 1;
         if (cx >= 0 && cy >= 0 && cz >= 0 && cx < (int)P.nbx && cy < (int)P.nby && cz < (int)P.nbz)

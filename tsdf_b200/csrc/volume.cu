@@ -58,7 +58,11 @@ int allocate(tsdf_b200_volume *v, uint32_t nx, uint32_t ny, uint32_t nz, float p
     v->phys[0] = px; v->phys[1] = py; v->phys[2] = pz;
     tsdf_b200_volume_params(nx, ny, nz, v->phys, v->vs, &v->trunc);
     const size_t n = nvox(v);
-    TSDF_CUDA_TRY(cudaStreamCreateWithFlags(&v->stream, cudaStreamNonBlocking));
+    // A BLOCKING stream: distance_data() / weight_data() / deformation() hand raw device pointers to callers that work on
+    // the legacy default stream (the reference's marching cubes and raycaster kernels, SceneFusion writing the deformation
+    // grid); the legacy stream and a blocking stream order each other implicitly, as if everything ran on one stream
+    // like in the reference (which synchronises the device after every launch).
+    TSDF_CUDA_TRY(cudaStreamCreateWithFlags(&v->stream, cudaStreamDefault));
     TSDF_CUDA_TRY(cudaMalloc(&v->d_dist, n * sizeof(float)));
     TSDF_CUDA_TRY(cudaMalloc(&v->d_weight, n * sizeof(float)));
     TSDF_CUDA_TRY(cudaMalloc(&v->d_occ, tsdf_b200_occupancy_bytes(nx, ny, nz)));
@@ -137,6 +141,15 @@ extern "C" int tsdf_b200_volume_get(const tsdf_b200_volume *v, uint32_t size[3],
     }
     if (trunc) *trunc = v->trunc;
     if (max_weight) *max_weight = v->max_weight;
+    return 0;
+}
+
+extern "C" int tsdf_b200_volume_get_global(const tsdf_b200_volume *v, float translation[3], float rotation[3]) {
+    if (!v) return TSDF_B200_EINVAL;
+    for (int i = 0; i < 3; i++) {
+        if (translation) translation[i] = v->gtrans[i];
+        if (rotation) rotation[i] = v->grot[i];
+    }
     return 0;
 }
 

@@ -3,6 +3,7 @@
 #include "../../include/tsdf_b200.h"
 
 #include <cmath>
+#include <cstdint>
 #include <cstdlib>
 #include <iostream>
 #include <vector>
@@ -29,9 +30,13 @@ DepthImage *GPURaycaster::render_to_depth_image(const TSDFVolume &volume, const 
     std::vector<uint16_t> depth(pixels);
     for (size_t i = 0; i < pixels; i++) {
         const Eigen::Vector3f cam = camera.world_to_camera(Eigen::Vector3f{vertices(0, i), vertices(1, i), vertices(2, i)});
-        // (uint16_t)roundf(z) as the reference writes it (GPURaycaster.cu:579); NaN (no surface) is made an explicit 0
+        // (uint16_t)roundf(z) as the reference's host compiler evaluates it (GPURaycaster.cu:579): a truncating float ->
+        // int32 conversion (cvttss2si: NaN and out-of-range give INT32_MIN) whose low 16 bits are kept.  Written out so that
+        // the result does not depend on how this compiler treats the (formally undefined) out-of-range cast: a pixel
+        // without a surface (NaN vertex) is 0, a vertex behind the camera wraps like it does in the reference.
         const float z = std::round(cam.z());
-        depth[i] = (z == z && z > 0.0f && z < 65536.0f) ? static_cast<uint16_t>(z) : 0;
+        const int32_t zi = (z >= -2147483648.0f && z < 2147483648.0f) ? static_cast<int32_t>(z) : INT32_MIN;
+        depth[i] = static_cast<uint16_t>(static_cast<uint32_t>(zi) & 0xffffu);
     }
     return new DepthImage(m_width, m_height, depth.data());
 }

@@ -28,6 +28,10 @@ void TSDFVolume::refresh() {
     m_offset = float3{off[0], off[1], off[2]};
     m_truncation_distance = trunc;
     m_max_weight = max_weight;
+    float gt[3] = {0, 0, 0}, gr[3] = {0, 0, 0};
+    tsdf_b200_volume_get_global(m_impl, gt, gr);
+    m_global_translation = float3{gt[0], gt[1], gt[2]};
+    m_global_rotation = float3{gr[0], gr[1], gr[2]};
 }
 
 void TSDFVolume::release() {

@@ -62,6 +62,20 @@ def _ptr_array(ptrs):
     return (C.c_void_p * len(ptrs))(*ptrs)
 
 
+def _on_stream(method):
+    """Runs a ShardedEngine method with the engine's stream as torch's current stream, so that the torch-side operations
+    inside it (counter resets, collectives, .item() reads, copies) are ordered against the C-ABI kernel launches."""
+    import functools
+
+    @functools.wraps(method)
+    def wrapped(self, *a, **kw):
+        if torch.cuda.current_stream().cuda_stream == self._tstream.cuda_stream:
+            return method(self, *a, **kw)
+        with torch.cuda.stream(self._tstream):
+            return method(self, *a, **kw)
+    return wrapped
+
+
 class ShardedEngine:
     def __init__(self, n, physical, rank=0, world=1, stream=None, skipping=True, stage_depth=True, layout="contiguous", slab=16):
         """layout (world > 1): "contiguous" — one slab per rank (default); "interleaved" — global slabs of `slab` planes
@@ -74,7 +88,10 @@ class ShardedEngine:
         self.voxel, self.trunc = volume_params(self.n, self.physical)
         self.offset = np.zeros(3, np.float32)
         self.offset_at_clear = np.zeros(3, np.float32)
-        self.stream = C.c_void_p(stream if stream is not None else torch.cuda.current_stream().cuda_stream)
+        # Every torch-side operation of the engine (counter resets, collectives, D2H reads) must be ordered against the
+        # C-ABI launches: they all run with `self._tstream` current, which IS the stream the kernels are launched on.
+        self._tstream = torch.cuda.ExternalStream(stream) if stream is not None else torch.cuda.current_stream()
+        self.stream = C.c_void_p(self._tstream.cuda_stream)
         self.skipping = skipping
         self.stage_depth = stage_depth
         self._staged = None
@@ -126,10 +143,19 @@ class ShardedEngine:
             self.launches_per_step += 2 * (len(self.slabs) - 1)          # one integrate + one halo integrate per owned slab
 
     # ------------------------------------------------------------------------------------------
+    @_on_stream
     def clear(self):
         if self.layout in ("interleaved", "replica"):
             check(lib.tsdf_b200_clear(_ptr(self.dist), _ptr(self.weight), *self.local_n, self.trunc, None, self.stream), "clear")
             self.occ.zero_()
+            if self.replica is not None:
+                # the replica keeps whatever was pushed before the clear, and after it those bricks are no longer flagged,
+                # hence no longer pushed — yet the march still reads some of them (the low-edge layer; apron voxels of
+                # unflagged neighbours of a flagged brick): back to the fill value.  Ordering against the peers' pushes:
+                # their last push landed before the barrier that ended the previous raycast on this rank, and their next
+                # one follows the flag reduction of the next raycast, which this rank enters after this fill (same stream).
+                nv = self.n[0] * self.n[1] * self.n[2]
+                check(lib.tsdf_b200_fill_f32(C.c_void_p(self.replica), nv, self.trunc, self.stream), "fill")
         else:
             check(lib.tsdf_b200_clear(_ptr(self.dist), _ptr(self.weight), *self.local_n, self.trunc, _ptr(self.occ),
                                       self.stream), "clear")
@@ -161,6 +187,7 @@ class ShardedEngine:
             self._staged = torch.empty((need + 3) // 4, dtype=torch.float32, device="cuda")
         check(lib.tsdf_b200_depth_stage(_ptr(d_depth), w, h, _ptr(self._staged), self.stream), "depth_stage")
 
+    @_on_stream
     def integrate(self, d_depth, cam, count=False, restage=True):
         """d_depth: (H, W) uint16 CUDA tensor.  Returns voxels rewritten (owned planes only) when count.
         restage=False reuses the staged frame of the previous call (same depth frame; kernel-timing aid)."""
@@ -210,6 +237,7 @@ class ShardedEngine:
             return int(self.counters[0].item())
         return None
 
+    @_on_stream
     def march(self, w, h, cam, count=False):
         """Sharded raycast, phase 1: this rank's keys (k_hit << 32 | sample bits, INT64_MAX = no hit in my planes)."""
         self._buffers(w, h)
@@ -230,6 +258,7 @@ class ShardedEngine:
                   "raycast_slab")
         return self.keys
 
+    @_on_stream
     def resolve(self, w, h, cam):
         """Sharded raycast, phase 2: min-reduced keys (in self.keys) -> vertices and normals."""
         _, _, kinv_p, origin_p, rot_p, _ = self._mats(cam)
@@ -240,6 +269,7 @@ class ShardedEngine:
         check(lib.tsdf_b200_normals(w, h, _ptr(self.vertices), _ptr(self.normals), self.stream), "normals")
 
     # ---- layout="replica": image-sharded raycast over peer memory ------------------------------------------------------
+    @_on_stream
     def connect(self, w, h, peers=None):
         """Allocates this rank's shareable vertex map and learns every rank's replica and vertex map.  peers: the engines
         of all ranks when they live in this process (tests emulate the ranks on one GPU); otherwise the CUDA IPC handles
@@ -279,6 +309,7 @@ class ShardedEngine:
         nb = ((self.n[0] + BRICK - 1) // BRICK) * ((self.n[1] + BRICK - 1) // BRICK) * ((self.n[2] + BRICK - 1) // BRICK)
         return self.occ[:nb]
 
+    @_on_stream
     def push(self, count=False):
         """Copies the owned surface bricks into every rank's replica (flags must be merged first)."""
         if count:
@@ -290,6 +321,7 @@ class ShardedEngine:
             return int(self.counters[1].item())
         return None
 
+    @_on_stream
     def march_tiles(self, w, h, cam, count=False):
         """Marches this rank's pixel tiles against its replica and stores the vertices into every rank's vertex map."""
         _, _, kinv_p, origin_p, rot_p, _ = self._mats(cam)
@@ -308,6 +340,7 @@ class ShardedEngine:
         import torch.distributed as dist
         dist.all_reduce(self._token)          # stream-ordered; the host does not wait
 
+    @_on_stream
     def raycast(self, w, h, cam, count=False):
         if self.layout == "replica":
             import torch.distributed as dist
@@ -348,6 +381,7 @@ class ShardedEngine:
             return int(self.counters[1].item())
         return None
 
+    @_on_stream
     def extract_mesh(self):
         """Marching cubes of this rank's owned planes (tsdf_b200_mc_extract; the halo plane closes the cubes at the slab's
         upper face).  Returns a (n, 3) float32 CUDA tensor: three consecutive vertices per triangle, in the reference's
@@ -366,6 +400,7 @@ class ShardedEngine:
             lib.tsdf_b200_device_free(out)
         return mesh
 
+    @_on_stream
     def last_ray_stats(self):
         """Hit pixels / NaN pixels of the last raycast (diagnostics for the bench line)."""
         if self._pix == 0:
@@ -374,6 +409,7 @@ class ShardedEngine:
         hits = int((~torch.isnan(v)).sum().item())
         return {"hit_pixels": hits, "pixels": self._pix}
 
+    @_on_stream
     def e2e(self, frames, cams, warmup, steps, w, h):
         """Host-buffer loop for the sharded case: pinned depth H2D on every rank, result D2H on rank 0."""
         import time
@@ -409,6 +445,7 @@ class ShardedEngine:
                 "d2h_bytes_per_step": 2 * w * h * 3 * 4, "ms_per_step": ms,
                 "api": "ShardedEngine: pinned depth H2D on every rank, integrate+raycast, vertex+normal D2H on rank 0"}
 
+    @_on_stream
     def read_local(self):
         torch.cuda.synchronize()
         return self.dist.cpu().numpy(), self.weight.cpu().numpy()

@@ -286,7 +286,7 @@ def main():
             frames.append(depth)
         d_frames = [torch.from_numpy(f).cuda() for f in frames]
         slab = args.slab if args.slab > 0 else max(8, (size // max(world, 1)) // 8 * 8)
-        eng = sharded.ShardedEngine(n, PHYS, rank, world, stream=stream.cuda_stream, layout=args.layout, slab=slab)
+        eng = sharded.ShardedEngine(n, PHYS, rank, world, stream=stream, layout=args.layout, slab=slab)
         for i in range(Wm):
             eng.integrate(d_frames[i], cams[i])
             eng.raycast(W, H, cams[i])
@@ -335,6 +335,7 @@ def main():
                 ts = []
                 for _ in range(5):
                     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    torch.cuda._sleep(400000)     # the launches queue up behind a busy GPU: the events bracket device time only
                     a.record(stream); eng.integrate(d, cam, restage=False); b.record(stream)
                     torch.cuda.synchronize()
                     ts.append(a.elapsed_time(b))

@@ -90,7 +90,15 @@ class ShardedEngine:
         self.offset_at_clear = np.zeros(3, np.float32)
         # Every torch-side operation of the engine (counter resets, collectives, D2H reads) must be ordered against the
         # C-ABI launches: they all run with `self._tstream` current, which IS the stream the kernels are launched on.
-        self._tstream = torch.cuda.ExternalStream(stream) if stream is not None else torch.cuda.current_stream()
+        # `stream`: None (torch's current stream), a torch.cuda.Stream, or a raw cudaStream_t as an int (0 = legacy default).
+        if stream is None:
+            self._tstream = torch.cuda.current_stream()
+        elif isinstance(stream, torch.cuda.Stream):
+            self._tstream = stream
+        elif int(stream) == 0:
+            self._tstream = torch.cuda.default_stream()
+        else:
+            self._tstream = torch.cuda.ExternalStream(int(stream))
         self.stream = C.c_void_p(self._tstream.cuda_stream)
         self.skipping = skipping
         self.stage_depth = stage_depth

@@ -6,13 +6,13 @@ NVCC      ?= /usr/local/cuda/bin/nvcc
 ARCH      := -gencode arch=compute_100a,code=sm_100a
 NVCCFLAGS := $(ARCH) -O3 -std=c++17 -lineinfo -fmad=false -Xcompiler -fPIC,-Wall,-Wno-unused-function
 CSRC      := tsdf_b200/csrc
-OBJS      := $(CSRC)/integrate.o $(CSRC)/raycast.o $(CSRC)/misc.o $(CSRC)/volume.o $(CSRC)/mc.o $(CSRC)/bilateral.o $(CSRC)/exchange.o
+OBJS      := $(CSRC)/integrate.o $(CSRC)/raycast.o $(CSRC)/misc.o $(CSRC)/volume.o $(CSRC)/mc.o $(CSRC)/bilateral.o $(CSRC)/exchange.o $(CSRC)/multi.o
 
 all: lib oracle classes
 
 lib: tsdf_b200/libtsdf_b200.so
 
-$(CSRC)/%.o: $(CSRC)/%.cu $(CSRC)/common.cuh $(CSRC)/integrate_rigid.cuh $(CSRC)/mc_tables.h include/tsdf_b200.h
+$(CSRC)/%.o: $(CSRC)/%.cu $(CSRC)/common.cuh $(CSRC)/integrate_rigid.cuh $(CSRC)/mc_tables.h $(CSRC)/volume_internal.h include/tsdf_b200.h
 	$(NVCC) $(NVCCFLAGS) -c $< -o $@
 
 # instrumented build of the raycast for tools/ray_iters.py (per-ray iteration classes, per-tile clocks); not the product
@@ -20,6 +20,11 @@ dbg: tsdf_b200/libtsdf_b200_dbg.so
 tsdf_b200/libtsdf_b200_dbg.so: $(OBJS)
 	$(NVCC) $(NVCCFLAGS) -DTSDF_RAY_DEBUG -c $(CSRC)/raycast.cu -o $(CSRC)/raycast_dbg.o
 	$(NVCC) $(ARCH) -shared -o $@ $(subst raycast.o,raycast_dbg.o,$(OBJS))
+
+# tuning variants of the raycast (A/B runs through TSDF_B200_LIB): make variant NAME=minb5 RAYFLAGS=-DTSDF_RAY_MINB=5
+variant: $(OBJS)
+	$(NVCC) $(NVCCFLAGS) $(RAYFLAGS) -c $(CSRC)/raycast.cu -o $(CSRC)/raycast_$(NAME).o
+	$(NVCC) $(ARCH) -shared -o tsdf_b200/libtsdf_b200_$(NAME).so $(subst raycast.o,raycast_$(NAME).o,$(OBJS))
 
 tsdf_b200/libtsdf_b200.so: $(OBJS)
 	$(NVCC) $(ARCH) -shared -o $@ $(OBJS)
@@ -61,4 +66,4 @@ ref:
 clean:
 	rm -f $(CSRC)/*.o $(HOST)/*.o tsdf_b200/libtsdf_b200.so tsdf_b200/libtsdf_b200_classes.so oracle/liboracle.so
 
-.PHONY: all lib oracle ref clean classes kinfu
+.PHONY: all lib oracle ref clean classes kinfu variant dbg

@@ -52,6 +52,8 @@ def parse():
     ap.add_argument("--size", type=int, default=512, help="voxels per side (512 = the headline workload)")
     ap.add_argument("--layout", default="contiguous", choices=["contiguous", "interleaved", "replica"],
                     help="multi-GPU layout (tsdf_b200/sharded.py): Z-slabs + key exchange, or surface replicas + image tiles")
+    ap.add_argument("--exchange", default="peer", choices=["peer", "allreduce"],
+                    help="multi-GPU key exchange of the contiguous layout: atomics into rank 0's key map over NVLink, or NCCL all-reduce(min)")
     ap.add_argument("--slab", type=int, default=0, help="planes per slab for the interleaved / replica layouts (0: size / gpus)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -286,7 +288,7 @@ def main():
             frames.append(depth)
         d_frames = [torch.from_numpy(f).cuda() for f in frames]
         slab = args.slab if args.slab > 0 else max(8, (size // max(world, 1)) // 8 * 8)
-        eng = sharded.ShardedEngine(n, PHYS, rank, world, stream=stream, layout=args.layout, slab=slab)
+        eng = sharded.ShardedEngine(n, PHYS, rank, world, stream=stream, layout=args.layout, slab=slab, exchange=args.exchange)
         for i in range(Wm):
             eng.integrate(d_frames[i], cams[i])
             eng.raycast(W, H, cams[i])

@@ -97,6 +97,10 @@ int tsdf_b200_integrate(float *d_dist, float *d_weight, const float *d_deform,
 /* Test hook: tsdf_b200_integrate picks a specialised kernel when the camera is rigid with a
  * conventional K (same result bits, fewer instructions); on != 0 forces the general kernel.  */
 void tsdf_b200_debug_force_generic_integrate(int on);
+/* Test / measurement hook: how the rigid-camera kernel stages the dist / weight planes.  0 = per-thread cp.async, one pass
+ * (default); 1 = TMA boxes (cp.async.bulk.tensor + mbarrier; environment TSDF_B200_TMA=1); 2 = box cull into a work list +
+ * persistent kernel (TSDF_B200_LIST=1).  Same result bits in every variant.                                      */
+void tsdf_b200_debug_integrate_variant(int variant);
 
 /* Size in bytes of the occupancy buffer of a volume: three bytes per 8^3 brick — the brick flags that
  * integrate / occupancy_rebuild maintain, then the brick distance grid and a scratch copy that the
@@ -156,6 +160,19 @@ int tsdf_b200_raycast_slab(const float *d_dist_slab, uint32_t nx, uint32_t ny, u
                            uint32_t width, uint32_t height, const float *d_table,
                            const uint8_t *d_occ_slab, long long *d_keys,
                            unsigned long long *d_n_samples, int fastdiv, void *stream);
+
+/* tsdf_b200_raycast_slab with the exchange fused into the march: instead of writing a key per pixel, every ray that hits
+ * inside this slab min-merges its key into d_keys_min[pixel] with a 64-bit atomic — d_keys_min may be another GPU's key
+ * map (peer memory over NVLink: cudaDeviceEnablePeerAccess in one process, tsdf_b200_peer_open across processes), so the
+ * ranks of a sharded volume need no collective for the exchange, only a barrier before the owner of the map resolves it.
+ * The map must hold INT64_MAX in every pixel before the first rank starts (tsdf_b200_raycast_resolve_reset leaves it so).  */
+int tsdf_b200_raycast_slab_min(const float *d_dist_slab, uint32_t nx, uint32_t ny, uint32_t nz,
+                               uint32_t z_base, uint32_t z_planes, uint32_t z_lo, uint32_t z_hi,
+                               const float voxel[3], const float space_min[3], const float space_max[3],
+                               float trunc, const float origin[3], const float rot[9], const float kinv[9],
+                               uint32_t width, uint32_t height, const float *d_table,
+                               const uint8_t *d_occ_slab, long long *d_keys_min,
+                               unsigned long long *d_n_samples, int fastdiv, void *stream);
 
 /* Z-sharded raycast, march phase, INTERLEAVED slabs: the volume's planes are cut into global slabs of slab_planes planes
  * (a multiple of 8) dealt to `world` ranks round robin (slab s belongs to rank s % world) — surfaces then spread over the
@@ -218,6 +235,15 @@ int tsdf_b200_raycast_resolve(const long long *d_keys, const float space_min[3],
                               uint32_t width, uint32_t height, const float *d_table,
                               float *d_vertices, int32_t *d_khit, void *stream);
 
+/* tsdf_b200_raycast_resolve that also puts INT64_MAX back into every key it reads: the map is ready for the next frame's
+ * tsdf_b200_raycast_slab_min without a separate fill.                                                              */
+int tsdf_b200_raycast_resolve_reset(long long *d_keys, const float space_min[3], const float space_max[3],
+                                    float trunc, const float origin[3], const float rot[9], const float kinv[9],
+                                    uint32_t width, uint32_t height, const float *d_table,
+                                    float *d_vertices, int32_t *d_khit, void *stream);
+/* count 64-bit words <- value (key maps: INT64_MAX). */
+int tsdf_b200_fill_i64(long long *d_ptr, size_t count, long long value, void *stream);
+
 /* Replaces the compute_normals kernel (RayCaster/GPURaycaster.cu:393-427). */
 int tsdf_b200_normals(uint32_t width, uint32_t height, const float *d_vertices,
                       float *d_normals, void *stream);
@@ -263,6 +289,18 @@ typedef struct tsdf_b200_volume tsdf_b200_volume;
 /* TSDFVolume(UInt3, Float3) / set_size (TSDF/TSDFVolume.cu:430-437, 679-722). */
 int tsdf_b200_volume_create(uint32_t nx, uint32_t ny, uint32_t nz, float px, float py, float pz,
                             tsdf_b200_volume **out);
+/* The same volume sharded along Z over `ngpus` GPUs of the box, inside this process (csrc/multi.cu): GPU r owns a slab of
+ * whole 8-voxel bricks plus one redundant halo plane; integrate needs no communication, raycast min-merges the per-slab
+ * hits into GPU 0's key map with atomics over NVLink peer memory, marching cubes runs per slab.  Every entry point below
+ * works on such a volume and returns the same bits as on one GPU; exceptions: the deformation grid is not distributed
+ * (tsdf_b200_volume_deformation returns NULL, _set_deformation TSDF_B200_ESTATE), and distance_data() / weight_data()
+ * gather the slabs into a full-size array on GPU 0 at every call.  tsdf_b200_volume_create itself creates a sharded volume
+ * when the environment variable TSDF_NGPUS is > 1 — that is how the unchanged kinfu.cpp uses several GPUs.  Fewer GPUs or
+ * brick layers than asked for: as many slabs as fit (one = the single-GPU volume).                                   */
+int tsdf_b200_volume_create_sharded(uint32_t nx, uint32_t ny, uint32_t nz, float px, float py, float pz, int ngpus,
+                                    tsdf_b200_volume **out);
+/* GPUs the volume lives on (1 = not sharded). */
+int tsdf_b200_volume_gpus(const tsdf_b200_volume *v);
 /* TSDFVolume(const std::string&) load constructor (TSDF/TSDFVolume.cu:463-664). */
 int tsdf_b200_volume_load(const char *path, tsdf_b200_volume **out);
 void tsdf_b200_volume_destroy(tsdf_b200_volume *v);
@@ -302,6 +340,11 @@ int tsdf_b200_volume_raycast(const tsdf_b200_volume *v, uint32_t width, uint32_t
                              float *host_normals);
 /* TSDFVolume::save_to_file (TSDF/TSDFVolume.cu:911-1027), byte-compatible format. */
 int tsdf_b200_volume_save(const tsdf_b200_volume *v, const char *path);
+
+/* extract_surface_ms (MarchingCubes/MarkAndSweepMC.cu:390-497) of the volume: *d_vertices_out receives a cudaMalloc'ed array
+ * of 3 floats per vertex on the volume's (first) GPU, in the reference's order (tsdf_b200_mc_extract); release it with
+ * tsdf_b200_device_free.  A sharded volume extracts per slab and concatenates.                                    */
+int tsdf_b200_volume_extract_mesh(const tsdf_b200_volume *v, float **d_vertices_out, unsigned long long *n_vertices_out);
 
 /* Counters of the last integrate / raycast (voxels rewritten, samples evaluated). */
 int tsdf_b200_volume_stats(const tsdf_b200_volume *v, unsigned long long *n_updated,

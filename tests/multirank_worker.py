@@ -21,7 +21,7 @@ def main():
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     from tsdf_b200 import scenes, sharded
     size = int(sys.argv[1]) if len(sys.argv) > 1 else 128
-    layouts = sys.argv[2].split(",") if len(sys.argv) > 2 else ["contiguous", "interleaved", "replica"]
+    layouts = sys.argv[2].split(",") if len(sys.argv) > 2 else ["contiguous", "peer", "interleaved", "replica"]
     n, phys, w, h = (size,) * 3, (3000.0,) * 3, 640, 480
     frames = [0, 90, 333, 610]
     cams = [scenes.orbit_camera(f, 1000) for f in frames]
@@ -43,17 +43,21 @@ def main():
         return bool(((a == b) | nan).all().item())
 
     for layout in layouts:
-        slab = 16 if layout != "contiguous" else 0
-        eng = sharded.ShardedEngine(n, phys, rank, world, layout=layout, slab=slab or 16)
+        # "peer": the contiguous layout with the key exchange fused into the march (atomics into rank 0's map over NVLink);
+        # only rank 0 holds the result there
+        exchange = "peer" if layout == "peer" else "allreduce"
+        compare_here = layout != "peer" or rank == 0
+        layout = "contiguous" if layout == "peer" else layout
+        eng = sharded.ShardedEngine(n, phys, rank, world, layout=layout, slab=16, exchange=exchange)
         for i, (cam, d) in enumerate(zip(cams, depths)):
             eng.integrate(d, cam)
             eng.raycast(w, h, cam)
             torch.cuda.synchronize()
             dist.barrier()
-            if not same(eng.vertices, want[i][0]):
-                failures.append(f"{layout}: vertices of frame {frames[i]} differ on rank {rank}")
-            if not same(eng.normals, want[i][1]):
-                failures.append(f"{layout}: normals of frame {frames[i]} differ on rank {rank}")
+            if compare_here and not same(eng.vertices, want[i][0]):
+                failures.append(f"{layout}/{exchange}: vertices of frame {frames[i]} differ on rank {rank}")
+            if compare_here and not same(eng.normals, want[i][1]):
+                failures.append(f"{layout}/{exchange}: normals of frame {frames[i]} differ on rank {rank}")
         ld = eng.dist.view(-1, size * size).view(torch.int32)
         lw = eng.weight.view(-1, size * size).view(torch.int32)
         if layout == "contiguous":
@@ -73,8 +77,8 @@ def main():
         eng.integrate(depths[2], cams[2]); eng.raycast(w, h, cams[2])
         torch.cuda.synchronize()
         dist.barrier()
-        if not same(eng.vertices, whole2.vertices):
-            failures.append(f"{layout}: vertices after clear differ on rank {rank}")
+        if compare_here and not same(eng.vertices, whole2.vertices):
+            failures.append(f"{layout}/{exchange}: vertices after clear differ on rank {rank}")
         whole2.close()
         torch.cuda.synchronize()
         dist.barrier()

@@ -87,6 +87,20 @@ def test_config3_512_properties(G):
     assert torch.equal(a.occ[: a.occ.numel() // 3], g.occ[: g.occ.numel() // 3])
     del g
 
+    # (3b) the other staging variants of the rigid kernel — TMA boxes + mbarriers, and the two-pass work list — give the same bits
+    for variant in (1, 2):
+        g = G.DeviceVolume(n, phys)
+        G.lib.tsdf_b200_debug_integrate_variant(variant)
+        try:
+            for c, d in zip(cams, depths):
+                assert g.integrate(d, c.inv_pose, c.k, c.kinv) == counts[cams.index(c)]
+        finally:
+            G.lib.tsdf_b200_debug_integrate_variant(0)
+        assert torch.equal(a.dist.view(torch.int32), g.dist.view(torch.int32)), f"variant {variant}: dist"
+        assert torch.equal(a.weight.view(torch.int32), g.weight.view(torch.int32)), f"variant {variant}: weight"
+        assert torch.equal(a.occ[: a.occ.numel() // 3], g.occ[: g.occ.numel() // 3]), f"variant {variant}: brick flags"
+        del g
+
     # (4) raycast: skipping changes nothing but the number of samples evaluated
     cam = cams[1]
     V1, N1, k1, s1 = a.raycast(640, 480, cam.pose, cam.kinv, skip=True, fastdiv=True)

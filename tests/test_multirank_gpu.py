@@ -27,11 +27,11 @@ def _gpus():
 def test_two_ranks_equal_single_gpu(built):
     if _gpus() < 2:
         pytest.skip("needs 2 GPUs")
-    _run(2, 128, "contiguous,interleaved,replica", 29631)
+    _run(2, 128, "contiguous,peer,interleaved,replica", 29631)
 
 
 def test_all_ranks_equal_single_gpu(built):
     g = _gpus()
     if g < 4:
         pytest.skip("needs 4+ GPUs")
-    _run(8 if g >= 8 else 4, 256, "contiguous,replica", 29632)
+    _run(8 if g >= 8 else 4, 256, "contiguous,peer,replica", 29632)

@@ -56,6 +56,30 @@ def test_integrate_matches_oracle(G, n):
     assert_bits_equal(dv.weight.cpu().numpy(), ov.weight, "weight")
 
 
+@pytest.mark.parametrize("variant", [1, 2])
+def test_integrate_staging_variants_match_oracle(G, variant):
+    """The TMA-staged kernel (3-D tensor maps, cp.async.bulk.tensor boxes of 128 x 4 x 1 voxels, mbarriers; boxes that hang
+    over the volume's edge are clipped by the hardware) and the two-pass work-list form, on a ragged volume, against the
+    oracle bit for bit."""
+    from oracle import oracle
+    from tsdf_b200 import scenes
+    n = (132, 70, 37)
+    dv = G.DeviceVolume(n, (3000, 2200, 1400))
+    ov = oracle.OracleVolume(n, (3000, 2200, 1400))
+    G.lib.tsdf_b200_debug_integrate_variant(variant)
+    try:
+        for f in range(3):
+            cam = scenes.orbit_camera(f * 5 + 1, 16)
+            k, kinv = quarter_intrinsics(cam, 0.5)
+            depth = scenes.render_depth(cam, 320, 240)
+            assert dv.integrate(depth, cam.inv_pose, k, kinv) == ov.integrate(depth, cam.inv_pose, k, kinv)
+    finally:
+        G.lib.tsdf_b200_debug_integrate_variant(0)
+    assert float(ov.weight.sum()) > 1000
+    assert_bits_equal(dv.dist.cpu().numpy(), ov.dist, "dist")
+    assert_bits_equal(dv.weight.cpu().numpy(), ov.weight, "weight")
+
+
 def test_integrate_fast_path_equals_general_kernel(G):
     """The rigid-camera kernel (approximate reciprocal + certainty test, exact fallback) against the general
     kernel on poses chosen to put many projections near rounding boundaries: a fronto-parallel camera whose

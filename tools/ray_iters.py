@@ -24,7 +24,7 @@ def classes(cam):
     return out
 
 
-for f in (0, 60, 125, 500):
+for f in [int(x) for x in (sys.argv[1].split(",") if len(sys.argv) > 1 else "0,125,250,375,500,625".split(","))]:
     cam = scenes.orbit_camera(f, 1000)
     if "dbg" in os.environ.get("TSDF_B200_LIB", ""):
         c = classes(cam)

@@ -31,6 +31,7 @@ SIGNATURES = {
     "tsdf_b200_integrate": (C.c_int, [_vp, _vp, _vp, _u32, _u32, _u32, _f, _f, _f, C.c_float, _f, _f, _f,
                                       _u32, _u32, _vp, _vp, _u32, _u32, _u32, _vp, _vp, _vp]),
     "tsdf_b200_debug_force_generic_integrate": (None, [C.c_int]),
+    "tsdf_b200_debug_integrate_variant": (None, [C.c_int]),
     "tsdf_b200_occupancy_bytes": (C.c_size_t, [_u32, _u32, _u32]),
     "tsdf_b200_occupancy_rebuild": (C.c_int, [_vp, _u32, _u32, _u32, C.c_float, _vp, _vp]),
     "tsdf_b200_ray_table": (C.c_int, [C.c_float, _vp, _vp]),
@@ -42,6 +43,10 @@ SIGNATURES = {
                                              _vp, _vp, _vp, C.c_int, _vp]),
     "tsdf_b200_raycast_slab": (C.c_int, [_vp, _u32, _u32, _u32, _u32, _u32, _u32, _u32, _f, _f, _f, C.c_float, _f, _f, _f,
                                          _u32, _u32, _vp, _vp, _vp, _vp, C.c_int, _vp]),
+    "tsdf_b200_raycast_slab_min": (C.c_int, [_vp, _u32, _u32, _u32, _u32, _u32, _u32, _u32, _f, _f, _f, C.c_float, _f, _f, _f,
+                                             _u32, _u32, _vp, _vp, _vp, _vp, C.c_int, _vp]),
+    "tsdf_b200_raycast_resolve_reset": (C.c_int, [_vp, _f, _f, C.c_float, _f, _f, _f, _u32, _u32, _vp, _vp, _vp, _vp]),
+    "tsdf_b200_fill_i64": (C.c_int, [_vp, C.c_size_t, C.c_longlong, _vp]),
     "tsdf_b200_raycast_interleaved": (C.c_int, [_vp, _u32, _u32, _u32, _u32, _u32, _u32, _f, _f, _f, C.c_float, _f, _f, _f,
                                                 _u32, _u32, _vp, _vp, _vp, _vp, C.c_int, _vp]),
     "tsdf_b200_bricks_push": (C.c_int, [_vp, _u32, _u32, _u32, _u32, _u32, _u32, _vp, _u32, C.POINTER(_vp), _vp, _vp]),
@@ -62,6 +67,9 @@ SIGNATURES = {
     "tsdf_b200_device_free": (None, [_vp]),
     "tsdf_b200_copy_to_host": (C.c_int, [_vp, _vp, C.c_size_t]),
     "tsdf_b200_volume_create": (C.c_int, [_u32, _u32, _u32, C.c_float, C.c_float, C.c_float, C.POINTER(_vp)]),
+    "tsdf_b200_volume_create_sharded": (C.c_int, [_u32, _u32, _u32, C.c_float, C.c_float, C.c_float, C.c_int, C.POINTER(_vp)]),
+    "tsdf_b200_volume_gpus": (C.c_int, [_vp]),
+    "tsdf_b200_volume_extract_mesh": (C.c_int, [_vp, C.POINTER(_vp), _ull]),
     "tsdf_b200_volume_load": (C.c_int, [C.c_char_p, C.POINTER(_vp)]),
     "tsdf_b200_volume_destroy": (None, [_vp]),
     "tsdf_b200_volume_get": (C.c_int, [_vp, C.POINTER(_u32), _f, _f, _f, _f, _f]),
@@ -123,10 +131,13 @@ def volume_params(n, physical):
 class Volume:
     """Level-2 handle: the C-ABI equivalent of the reference's TSDFVolume object (host buffers)."""
 
-    def __init__(self, n, physical, handle=None):
+    def __init__(self, n, physical, handle=None, gpus=None):
         self._h = _vp()
         if handle is not None:
             self._h = handle
+        elif gpus is not None:
+            check(lib.tsdf_b200_volume_create_sharded(n[0], n[1], n[2], physical[0], physical[1], physical[2], int(gpus),
+                                                      C.byref(self._h)), "volume_create_sharded")
         else:
             check(lib.tsdf_b200_volume_create(n[0], n[1], n[2], physical[0], physical[1], physical[2],
                                               C.byref(self._h)), "volume_create")
@@ -215,6 +226,21 @@ class Volume:
         a, b = C.c_ulonglong(), C.c_ulonglong()
         check(lib.tsdf_b200_volume_stats(self._h, C.byref(a), C.byref(b)))
         return a.value, b.value
+
+    @property
+    def gpus(self):
+        return lib.tsdf_b200_volume_gpus(self._h)
+
+    def extract_mesh(self):
+        """(n, 3) float32 mesh vertices (three per triangle) of extract_surface, copied to the host."""
+        out = _vp()
+        count = C.c_ulonglong()
+        check(lib.tsdf_b200_volume_extract_mesh(self._h, C.byref(out), C.byref(count)), "extract_mesh")
+        v = np.empty((count.value, 3), np.float32)
+        if count.value:
+            check(lib.tsdf_b200_copy_to_host(v.ctypes.data, out, v.nbytes), "copy_to_host")
+            lib.tsdf_b200_device_free(out)
+        return v
 
     def save(self, path):
         check(lib.tsdf_b200_volume_save(self._h, os.fsencode(path)), "save")

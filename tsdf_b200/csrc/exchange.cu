@@ -72,9 +72,19 @@ __global__ void __launch_bounds__(256) fill_kernel(float *p, size_t n, float v) 
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) p[i] = v;
 }
 
+__global__ void __launch_bounds__(256) fill_i64_kernel(long long *p, size_t n, long long v) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) p[i] = v;
+}
+
 }  // namespace tsdf
 
 using namespace tsdf;
+
+extern "C" int tsdf_b200_fill_i64(long long *d_ptr, size_t count, long long value, void *stream) {
+    if (!d_ptr) return TSDF_B200_EINVAL;
+    fill_i64_kernel<<<148 * 4, 256, 0, (cudaStream_t)stream>>>(d_ptr, count, value);
+    return (int)cudaGetLastError();
+}
 
 extern "C" int tsdf_b200_bricks_push(const float *d_dist_local, uint32_t nx, uint32_t ny, uint32_t nz,
                                      uint32_t slab_planes, uint32_t world, uint32_t rank,

@@ -40,6 +40,9 @@ struct RayParams {
     float *vertices;
     int32_t *khit;
     long long *keys;
+    long long *keys_min;         // SLAB: hits are min-merged into this key map with atomics (may live on a peer GPU) instead of
+                                 // being written to `keys`; pixels without a hit in this slab write nothing
+    int reset_keys;              // resolve_kernel: put INT64_MAX back into every key it has read
     unsigned long long *n_samples;
     unsigned int *tile_counter;  // work counter for dynamic tile scheduling (zeroed before the launch) or nullptr
     // Continuation queue: the kernel's run time used to be the march of its slowest ray (~400 dependent loop iterations
@@ -599,8 +602,10 @@ raycast_kernel(const __grid_constant__ RayParams P) {
         if (queued) {
             // continue_kernel writes this pixel
         } else if (SLAB) {
-            // key: first hit along the ray wins an all-reduce(min); the sample value rides in the low word
-            P.keys[pix] = (kh >= 0) ? (((long long)kh << 32) | (long long)(uint32_t)__float_as_uint(s_hit)) : 0x7fffffffffffffffLL;
+            // key: first hit along the ray wins the min over the ranks; the sample value rides in the low word
+            const long long key = (kh >= 0) ? (((long long)kh << 32) | (long long)(uint32_t)__float_as_uint(s_hit)) : 0x7fffffffffffffffLL;
+            if (P.keys_min) { if (kh >= 0) atomicMin(P.keys_min + pix, key); }
+            else P.keys[pix] = key;
         } else if (P.n_out) {
             for (uint32_t d = 0; d < P.n_out; d++) {
                 float *v = P.out[d] + 3 * pix;
@@ -676,7 +681,8 @@ continue_kernel(const __grid_constant__ RayParams P) {
         }
         if (lane == 0) {
             if (SLAB) {
-                P.keys[pix] = key;
+                if (P.keys_min) { if (key != 0x7fffffffffffffffLL) atomicMin(P.keys_min + pix, key); }
+                else P.keys[pix] = key;
             } else {
                 float ip[3] = { CUDART_NAN_F, CUDART_NAN_F, CUDART_NAN_F };
                 int k_hit = -1;
@@ -719,6 +725,7 @@ resolve_kernel(const __grid_constant__ RayParams P) {
     }
     const size_t pix = (size_t)imy * P.width + imx;
     const long long key = P.keys[pix];
+    if (P.reset_keys) P.keys[pix] = 0x7fffffffffffffffLL;
     float ip[3] = { CUDART_NAN_F, CUDART_NAN_F, CUDART_NAN_F };
     int kh = -1;
     if (key != 0x7fffffffffffffffLL) {
@@ -838,7 +845,7 @@ static int fill_params(RayParams &P, const float *d_dist, uint32_t nx, uint32_t 
     P.occ_lo = trunc * kOccLoFrac; P.occ_hi = trunc * kOccHiFrac;
     P.z_base = 0; P.z_lo = 0; P.z_hi = nz;
     P.cyc_s = 0; P.cyc_g = 0; P.cyc_r = 0;
-    P.vertices = nullptr; P.khit = nullptr; P.keys = nullptr; P.n_samples = nullptr; P.tile_counter = nullptr;
+    P.vertices = nullptr; P.khit = nullptr; P.keys = nullptr; P.keys_min = nullptr; P.reset_keys = 0; P.n_samples = nullptr; P.tile_counter = nullptr;
     P.debug_iters = getenv("TSDF_B200_DEBUG_ITERS") ? atoi(getenv("TSDF_B200_DEBUG_ITERS")) : 0;
     P.tile_first = 0; P.tile_stride = 1; P.n_out = 0; P.mirror = nullptr;
     P.queue = nullptr; P.queue_count = nullptr; P.queue_cap = 0;
@@ -1000,6 +1007,28 @@ extern "C" int tsdf_b200_raycast_slab(const float *d_dist_slab, uint32_t nx, uin
     return launch_march<true>(P, fastdiv, (cudaStream_t)stream);
 }
 
+extern "C" int tsdf_b200_raycast_slab_min(const float *d_dist_slab, uint32_t nx, uint32_t ny, uint32_t nz,
+                                          uint32_t z_base, uint32_t z_planes, uint32_t z_lo, uint32_t z_hi,
+                                          const float voxel[3], const float space_min[3], const float space_max[3],
+                                          float trunc, const float origin[3], const float rot[9], const float kinv[9],
+                                          uint32_t width, uint32_t height, const float *d_table,
+                                          const uint8_t *d_occ_slab, long long *d_keys_min,
+                                          unsigned long long *d_n_samples, int fastdiv, void *stream) {
+    if (!d_dist_slab || !d_keys_min) return TSDF_B200_EINVAL;
+    if (z_lo < z_base || z_hi > nz || z_lo > z_hi || z_base + z_planes > nz || z_planes == 0) return TSDF_B200_EINVAL;
+    if (z_hi > z_lo && (z_hi < nz ? z_hi : nz - 1) > z_base + z_planes - 1) return TSDF_B200_EINVAL;
+    if (d_occ_slab && z_base % TSDF_B200_BRICK != 0) return TSDF_B200_EINVAL;
+    RayParams P;
+    int rc = fill_params(P, d_dist_slab, nx, ny, nz, voxel, space_min, space_max, trunc, origin, rot, kinv, width, height, d_table, &fastdiv);
+    if (rc) return rc;
+    P.occ = d_occ_slab;
+    const BrickDims nb = brick_dims(nx, ny, z_planes);
+    P.nbx = nb.bx; P.nby = nb.by; P.nbz = nb.bz;
+    P.z_base = z_base; P.z_lo = z_lo; P.z_hi = z_hi;
+    P.keys_min = d_keys_min; P.n_samples = d_n_samples;
+    return launch_march<true>(P, fastdiv, (cudaStream_t)stream);
+}
+
 extern "C" int tsdf_b200_raycast_interleaved(const float *d_dist_local, uint32_t nx, uint32_t ny, uint32_t nz,
                                              uint32_t slab_planes, uint32_t world, uint32_t rank,
                                              const float voxel[3], const float space_min[3], const float space_max[3],
@@ -1018,6 +1047,24 @@ extern "C" int tsdf_b200_raycast_interleaved(const float *d_dist_local, uint32_t
     P.cyc_s = slab_planes; P.cyc_g = world; P.cyc_r = rank;
     P.keys = d_keys; P.n_samples = d_n_samples;
     return launch_march<true>(P, fastdiv, (cudaStream_t)stream);
+}
+
+extern "C" int tsdf_b200_raycast_resolve_reset(long long *d_keys, const float space_min[3], const float space_max[3],
+                                               float trunc, const float origin[3], const float rot[9], const float kinv[9],
+                                               uint32_t width, uint32_t height, const float *d_table,
+                                               float *d_vertices, int32_t *d_khit, void *stream) {
+    if (!d_keys || !d_vertices) return TSDF_B200_EINVAL;
+    RayParams P;
+    int fastdiv = 0;
+    const float one[3] = { 1.f, 1.f, 1.f };
+    int rc = fill_params(P, nullptr, 1, 1, 1, one, space_min, space_max, trunc, origin, rot, kinv, width, height, d_table, &fastdiv);
+    if (rc) return rc;
+    P.keys = d_keys; P.reset_keys = 1;
+    P.vertices = d_vertices; P.khit = d_khit;
+    dim3 block(128);
+    dim3 grid((width + 15) / 16, (height + 7) / 8);
+    resolve_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(P);
+    return (int)cudaGetLastError();
 }
 
 extern "C" int tsdf_b200_raycast_resolve(const long long *d_keys, const float space_min[3], const float space_max[3],

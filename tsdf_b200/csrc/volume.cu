@@ -5,7 +5,7 @@
 // synchronous semantics, but device buffers are persistent (no per-call cudaMalloc/cudaFree),
 // work runs on one private stream, and the 24 B/voxel deformation array exists only when
 // somebody asks for it.
-#include "common.cuh"
+#include "volume_internal.h"
 #include <math.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -14,33 +14,14 @@
 
 // (tsdf_b200_raycast_ex is declared in include/tsdf_b200.h)
 
-struct tsdf_b200_volume {
-    uint32_t nx = 0, ny = 0, nz = 0;
-    float phys[3] = {0, 0, 0}, vs[3] = {0, 0, 0};
-    float off[3] = {0, 0, 0};          // m_offset
-    float off_clear[3] = {0, 0, 0};    // m_offset at the time clear() wrote the deformation grid
-    float trunc = 0, max_weight = 15.0f;
-    float gtrans[3] = {0, 0, 0}, grot[3] = {0, 0, 0};
-    float *d_dist = nullptr, *d_weight = nullptr;
-    float *d_deform = nullptr;         // 6 floats / voxel, lazily materialised
-    bool deform_identity = true;       // d_deform (if any) equals the grid clear() would write
-    uint8_t *h_colour = nullptr;       // colours are never touched on the hot path; host copy only when loaded
-    uint8_t *d_occ = nullptr;
-    float *d_table = nullptr;
-    uint16_t *d_depth = nullptr; size_t depth_cap = 0;
-    float *d_staged = nullptr; size_t staged_cap = 0;   // staged depth frame (tsdf_b200_depth_stage)
-    float *d_vn = nullptr; size_t pix_cap = 0;   // vertices then normals
-    unsigned long long *d_counters = nullptr;    // [0] voxels rewritten, [1] samples
-    unsigned long long h_counters[2] = {0, 0};
-    cudaStream_t stream = nullptr;
-    int fastdiv = 0, skipping = 1, counting = 1;
-};
-
 namespace {
 
 size_t nvox(const tsdf_b200_volume *v) { return (size_t)v->nx * v->ny * v->nz; }
 
 void release(tsdf_b200_volume *v) {
+    if (v->multi) tsdf::multi_destroy(v);
+    cudaFreeHost(v->h_depth_pin); cudaFreeHost(v->h_vn_pin);
+    v->h_depth_pin = nullptr; v->h_vn_pin = nullptr; v->depth_pin_cap = v->vn_pin_cap = 0;
     cudaFree(v->d_dist); cudaFree(v->d_weight); cudaFree(v->d_deform); cudaFree(v->d_occ);
     cudaFree(v->d_table); cudaFree(v->d_depth); cudaFree(v->d_staged); cudaFree(v->d_vn); cudaFree(v->d_counters);
     free(v->h_colour);
@@ -49,7 +30,7 @@ void release(tsdf_b200_volume *v) {
     v->d_depth = nullptr; v->d_staged = nullptr; v->d_vn = nullptr; v->d_counters = nullptr; v->h_colour = nullptr; v->stream = nullptr;
 }
 
-int allocate(tsdf_b200_volume *v, uint32_t nx, uint32_t ny, uint32_t nz, float px, float py, float pz) {
+int allocate(tsdf_b200_volume *v, uint32_t nx, uint32_t ny, uint32_t nz, float px, float py, float pz, int ngpus) {
     // set_size (TSDFVolume.cu:679-722) takes uint16_t dimensions; the raycast indexes in 32 bits.
     if (nx == 0 || ny == 0 || nz == 0 || nx > 65535 || ny > 65535 || nz > 65535) return TSDF_B200_EINVAL;
     if (!(px != 0 && py != 0 && pz != 0)) return TSDF_B200_EINVAL;
@@ -57,7 +38,13 @@ int allocate(tsdf_b200_volume *v, uint32_t nx, uint32_t ny, uint32_t nz, float p
     v->nx = nx; v->ny = ny; v->nz = nz;
     v->phys[0] = px; v->phys[1] = py; v->phys[2] = pz;
     tsdf_b200_volume_params(nx, ny, nz, v->phys, v->vs, &v->trunc);
+    if (ngpus > 1) {
+        // Z-slabs over several GPUs (multi.cu); falls back to one GPU when the box or the volume has room for one slab only
+        const int rc = tsdf::multi_create(v, ngpus);
+        if (rc != TSDF_B200_EINVAL) return rc;
+    }
     const size_t n = nvox(v);
+    TSDF_CUDA_TRY(cudaGetDevice(&v->device));
     // A BLOCKING stream: distance_data() / weight_data() / deformation() hand raw device pointers to callers that work on
     // the legacy default stream (the reference's marching cubes and raycaster kernels, SceneFusion writing the deformation
     // grid); the legacy stream and a blocking stream order each other implicitly, as if everything ran on one stream
@@ -87,6 +74,7 @@ int allocate(tsdf_b200_volume *v, uint32_t nx, uint32_t ny, uint32_t nz, float p
 
 int ensure_deformation(tsdf_b200_volume *v) {
     if (v->d_deform) return 0;
+    if (v->multi) TSDF_CUDA_TRY(cudaSetDevice(v->device));     // materialised on GPU 0 (save_to_file writes it)
     TSDF_CUDA_TRY(cudaMalloc(&v->d_deform, nvox(v) * 6 * sizeof(float)));
     int rc = tsdf_b200_init_deformation(v->d_deform, v->nx, v->ny, v->nz, v->vs, v->off_clear, v->stream);
     if (rc) return rc;
@@ -98,6 +86,15 @@ int ensure_deformation(tsdf_b200_volume *v) {
 
 extern "C" int tsdf_b200_volume_clear(tsdf_b200_volume *v) {
     if (!v) return TSDF_B200_EINVAL;
+    if (v->multi) {
+        int rc = tsdf::multi_clear(v);
+        if (rc) return rc;
+        for (int i = 0; i < 3; i++) v->off_clear[i] = v->off[i];
+        v->deform_identity = true;
+        cudaSetDevice(v->device);
+        if (v->d_deform) { cudaFree(v->d_deform); v->d_deform = nullptr; }
+        return 0;
+    }
     int rc = tsdf_b200_clear(v->d_dist, v->d_weight, v->nx, v->ny, v->nz, v->trunc, v->d_occ, v->stream);
     if (rc) return rc;
     // clear() rewrites the deformation grid with the CURRENT offset (TSDFVolume.cu:839-841).
@@ -111,13 +108,39 @@ extern "C" int tsdf_b200_volume_clear(tsdf_b200_volume *v) {
     return 0;
 }
 
+// GPUs a volume is created on when the caller does not say: TSDF_NGPUS (default 1) — this is how the unchanged kinfu.cpp,
+// which only knows `TSDFVolume(size, physical_size)`, gets a volume sharded over the GPUs of the box.
+static int env_gpus() {
+    const char *e = getenv("TSDF_NGPUS");
+    const int n = e ? atoi(e) : 1;
+    return n > 1 ? n : 1;
+}
+
+extern "C" int tsdf_b200_volume_create_sharded(uint32_t nx, uint32_t ny, uint32_t nz, float px, float py, float pz, int ngpus,
+                                               tsdf_b200_volume **out) {
+    if (!out) return TSDF_B200_EINVAL;
+    *out = nullptr;
+    tsdf_b200_volume *v = new (std::nothrow) tsdf_b200_volume();
+    if (!v) return TSDF_B200_ENOMEM;
+    int rc = allocate(v, nx, ny, nz, px, py, pz, ngpus);
+    if (!rc) rc = tsdf_b200_volume_clear(v);
+    if (rc) { release(v); delete v; return rc; }
+    *out = v;
+    return 0;
+}
+
+extern "C" int tsdf_b200_volume_gpus(const tsdf_b200_volume *v) {
+    if (!v) return 0;
+    return v->multi ? (int)v->multi->shards.size() : 1;
+}
+
 extern "C" int tsdf_b200_volume_create(uint32_t nx, uint32_t ny, uint32_t nz, float px, float py, float pz,
                                        tsdf_b200_volume **out) {
     if (!out) return TSDF_B200_EINVAL;
     *out = nullptr;
     tsdf_b200_volume *v = new (std::nothrow) tsdf_b200_volume();
     if (!v) return TSDF_B200_ENOMEM;
-    int rc = allocate(v, nx, ny, nz, px, py, pz);
+    int rc = allocate(v, nx, ny, nz, px, py, pz, env_gpus());
     if (!rc) rc = tsdf_b200_volume_clear(v);
     if (rc) { release(v); delete v; return rc; }
     *out = v;
@@ -159,11 +182,25 @@ extern "C" int tsdf_b200_volume_set_offset(tsdf_b200_volume *v, float ox, float 
     return 0;
 }
 
-extern "C" const float *tsdf_b200_volume_distance_data(const tsdf_b200_volume *v) { return v ? v->d_dist : nullptr; }
-extern "C" const float *tsdf_b200_volume_weight_data(const tsdf_b200_volume *v) { return v ? v->d_weight : nullptr; }
+// Sharded volume: the slabs are gathered into a full-size array on GPU 0 at every call (the reference's callers of these
+// pointers — its marching cubes and raycaster kernels — are replaced by tsdf_b200_volume_extract_mesh / _raycast, which work
+// on the slabs where they are; the gather exists for completeness of the class surface).
+extern "C" const float *tsdf_b200_volume_distance_data(const tsdf_b200_volume *cv) {
+    if (!cv) return nullptr;
+    if (!cv->multi) return cv->d_dist;
+    tsdf_b200_volume *v = const_cast<tsdf_b200_volume *>(cv);
+    return tsdf::multi_gather_device(v) ? nullptr : v->multi->d_full_dist;
+}
+extern "C" const float *tsdf_b200_volume_weight_data(const tsdf_b200_volume *cv) {
+    if (!cv) return nullptr;
+    if (!cv->multi) return cv->d_weight;
+    tsdf_b200_volume *v = const_cast<tsdf_b200_volume *>(cv);
+    return tsdf::multi_gather_device(v) ? nullptr : v->multi->d_full_weight;
+}
 
 extern "C" float *tsdf_b200_volume_deformation(tsdf_b200_volume *v) {
-    if (!v || ensure_deformation(v)) return nullptr;
+    // a sharded volume is rigid-only: the deformation grid (SceneFusion's non-rigid path) is not distributed
+    if (!v || v->multi || ensure_deformation(v)) return nullptr;
     // The caller holds a writable device pointer from now on (SceneFusion writes through it):
     // stop assuming the identity grid.
     v->deform_identity = false;
@@ -172,6 +209,7 @@ extern "C" float *tsdf_b200_volume_deformation(tsdf_b200_volume *v) {
 
 extern "C" int tsdf_b200_volume_set_distance_data(tsdf_b200_volume *v, const float *host) {
     if (!v || !host) return TSDF_B200_EINVAL;
+    if (v->multi) return tsdf::multi_write(v, host, nullptr);
     TSDF_CUDA_TRY(cudaMemcpyAsync(v->d_dist, host, nvox(v) * sizeof(float), cudaMemcpyHostToDevice, v->stream));
     int rc = tsdf_b200_occupancy_rebuild(v->d_dist, v->nx, v->ny, v->nz, v->trunc, v->d_occ, v->stream);
     if (rc) return rc;
@@ -181,6 +219,7 @@ extern "C" int tsdf_b200_volume_set_distance_data(tsdf_b200_volume *v, const flo
 
 extern "C" int tsdf_b200_volume_set_weight_data(tsdf_b200_volume *v, const float *host) {
     if (!v || !host) return TSDF_B200_EINVAL;
+    if (v->multi) return tsdf::multi_write(v, nullptr, host);
     TSDF_CUDA_TRY(cudaMemcpyAsync(v->d_weight, host, nvox(v) * sizeof(float), cudaMemcpyHostToDevice, v->stream));
     TSDF_CUDA_TRY(cudaStreamSynchronize(v->stream));
     return 0;
@@ -188,6 +227,7 @@ extern "C" int tsdf_b200_volume_set_weight_data(tsdf_b200_volume *v, const float
 
 extern "C" int tsdf_b200_volume_set_deformation(tsdf_b200_volume *v, const float *host_nodes) {
     if (!v || !host_nodes) return TSDF_B200_EINVAL;
+    if (v->multi) return TSDF_B200_ESTATE;                 // rigid-only when sharded
     if (!v->d_deform) TSDF_CUDA_TRY(cudaMalloc(&v->d_deform, nvox(v) * 6 * sizeof(float)));
     TSDF_CUDA_TRY(cudaMemcpyAsync(v->d_deform, host_nodes, nvox(v) * 6 * sizeof(float), cudaMemcpyHostToDevice, v->stream));
     TSDF_CUDA_TRY(cudaStreamSynchronize(v->stream));
@@ -197,6 +237,7 @@ extern "C" int tsdf_b200_volume_set_deformation(tsdf_b200_volume *v, const float
 
 extern "C" int tsdf_b200_volume_read(const tsdf_b200_volume *v, float *host_dist, float *host_weight) {
     if (!v) return TSDF_B200_EINVAL;
+    if (v->multi) return tsdf::multi_read(v, host_dist, host_weight);
     if (host_dist) TSDF_CUDA_TRY(cudaMemcpyAsync(host_dist, v->d_dist, nvox(v) * sizeof(float), cudaMemcpyDeviceToHost, v->stream));
     if (host_weight) TSDF_CUDA_TRY(cudaMemcpyAsync(host_weight, v->d_weight, nvox(v) * sizeof(float), cudaMemcpyDeviceToHost, v->stream));
     TSDF_CUDA_TRY(cudaStreamSynchronize(v->stream));
@@ -206,6 +247,7 @@ extern "C" int tsdf_b200_volume_read(const tsdf_b200_volume *v, float *host_dist
 extern "C" int tsdf_b200_volume_integrate(tsdf_b200_volume *v, const uint16_t *host_depth, uint32_t width, uint32_t height,
                                           const float inv_pose[16], const float k[9], const float kinv[9]) {
     if (!v || !host_depth || !inv_pose || !k || !kinv || width == 0 || height == 0) return TSDF_B200_EINVAL;
+    if (v->multi) return tsdf::multi_integrate(v, host_depth, width, height, inv_pose, k, kinv);
     const size_t npix = (size_t)width * height;
     if (npix > v->depth_cap) {
         cudaFree(v->d_depth); v->d_depth = nullptr; v->depth_cap = 0;
@@ -238,6 +280,7 @@ extern "C" int tsdf_b200_volume_raycast(const tsdf_b200_volume *cv, uint32_t wid
                                         const float kinv[9], float *host_vertices, float *host_normals) {
     tsdf_b200_volume *v = const_cast<tsdf_b200_volume *>(cv);   // scratch buffers only; logical state is untouched
     if (!v || !pose || !kinv || !host_vertices || !host_normals || width == 0 || height == 0) return TSDF_B200_EINVAL;
+    if (v->multi) return tsdf::multi_raycast(v, width, height, pose, kinv, host_vertices, host_normals);
     const size_t npix = (size_t)width * height;
     if (npix > v->pix_cap) {
         cudaFree(v->d_vn); v->d_vn = nullptr; v->pix_cap = 0;
@@ -314,10 +357,9 @@ extern "C" int tsdf_b200_volume_save(const tsdf_b200_volume *cv, const char *pat
     ok &= fwrite(&v->max_weight, 4, 1, f) == 1;
     ok &= fwrite(v->gtrans, 4, 3, f) == 3;
     ok &= fwrite(v->grot, 4, 3, f) == 3;
-    cudaError_t e = cudaMemcpy(h, v->d_dist, n * 4, cudaMemcpyDeviceToHost);
-    ok &= e == cudaSuccess && fwrite(h, 4, n, f) == n;
-    e = cudaMemcpy(h, v->d_weight, n * 4, cudaMemcpyDeviceToHost);
-    ok &= e == cudaSuccess && fwrite(h, 4, n, f) == n;
+    ok &= tsdf_b200_volume_read(v, h, nullptr) == 0 && fwrite(h, 4, n, f) == n;        // (gathers the slabs of a sharded volume)
+    ok &= tsdf_b200_volume_read(v, nullptr, h) == 0 && fwrite(h, 4, n, f) == n;
+    cudaError_t e = cudaSuccess;
     if (v->h_colour) {
         ok &= fwrite(v->h_colour, 3, n, f) == n;
     } else {   // the reference never initialises colours (TSDFVolume.cu:835); write zeros
@@ -343,7 +385,8 @@ extern "C" int tsdf_b200_volume_load(const char *path, tsdf_b200_volume **out) {
     if (!ok) { fclose(f); return TSDF_B200_EIO; }
     tsdf_b200_volume *v = new (std::nothrow) tsdf_b200_volume();
     if (!v) { fclose(f); return TSDF_B200_ENOMEM; }
-    int rc = allocate(v, size[0], size[1], size[2], phys[0], phys[1], phys[2]);
+    // a file carries its own deformation grid, which is used verbatim: one GPU (sharded volumes are rigid-only)
+    int rc = allocate(v, size[0], size[1], size[2], phys[0], phys[1], phys[2], 1);
     if (rc) { fclose(f); release(v); delete v; return rc; }
     // The load constructor recomputes only the voxel size; everything else is taken from the file.
     for (int i = 0; i < 3; i++) { v->off[i] = off[i]; v->off_clear[i] = 0.f; v->gtrans[i] = gt[i]; v->grot[i] = gr[i]; }
@@ -370,4 +413,15 @@ extern "C" int tsdf_b200_volume_load(const char *path, tsdf_b200_volume **out) {
     if (!ok || rc) { release(v); delete v; return rc ? rc : (e != cudaSuccess ? (int)e : TSDF_B200_EIO); }
     *out = v;
     return 0;
+}
+
+// extract_surface_ms of the reference (MarchingCubes/MarkAndSweepMC.cu:390-497) on the volume object: one call for a whole
+// volume on one GPU, per slab and concatenated in slab order (= the reference's cube order) when the volume is sharded.
+extern "C" int tsdf_b200_volume_extract_mesh(const tsdf_b200_volume *cv, float **d_vertices_out, unsigned long long *n_vertices_out) {
+    tsdf_b200_volume *v = const_cast<tsdf_b200_volume *>(cv);
+    if (!v || !d_vertices_out || !n_vertices_out) return TSDF_B200_EINVAL;
+    *d_vertices_out = nullptr;
+    *n_vertices_out = 0;
+    if (v->multi) return tsdf::multi_extract_mesh(v, d_vertices_out, n_vertices_out);
+    return tsdf_b200_mc_extract(v->d_dist, v->nx, v->ny, v->nz, 0, 0, v->nz - 1, v->vs, v->off, d_vertices_out, n_vertices_out, v->stream);
 }

@@ -13,12 +13,10 @@ void extract_surface_ms(const TSDFVolume *const volume, int &num_vertices, float
     d_mesh_vertices = nullptr;
     d_mesh_vertex_voxel_indices = nullptr;
     d_mesh_vertex_voxel_count = nullptr;
-    const TSDFVolume::UInt3 size = volume->size();
-    const TSDFVolume::Float3 voxel = volume->voxel_size(), offset = volume->offset();
-    const float vs[3] = {voxel.x, voxel.y, voxel.z}, off[3] = {offset.x, offset.y, offset.z};
     float *d_vertices = nullptr;
     unsigned long long count = 0;
-    const int rc = tsdf_b200_mc_extract(volume->distance_data(), size.x, size.y, size.z, 0, 0, size.z - 1, vs, off, &d_vertices, &count, nullptr);
+    // through the volume object: a volume sharded over several GPUs (TSDF_NGPUS) extracts per slab
+    const int rc = tsdf_b200_volume_extract_mesh(volume->c_abi(), &d_vertices, &count);
     if (rc != 0) {
         std::cerr << "Marching cubes failed" << std::endl << tsdf_b200_strerror(rc) << std::endl;
         std::exit(-1);

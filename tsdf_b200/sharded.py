@@ -77,11 +77,16 @@ def _on_stream(method):
 
 
 class ShardedEngine:
-    def __init__(self, n, physical, rank=0, world=1, stream=None, skipping=True, stage_depth=True, layout="contiguous", slab=16):
+    def __init__(self, n, physical, rank=0, world=1, stream=None, skipping=True, stage_depth=True, layout="contiguous", slab=16,
+                 exchange="allreduce"):
         """layout (world > 1): "contiguous" — one slab per rank (default); "interleaved" — global slabs of `slab` planes
         dealt round robin so that surfaces spread over the ranks.  Interleaving is exact (tests) but measured slower at
         512^3 on 2-8 GPUs: the integrate turns into many sub-wave launches and every rank walks
-        every ray end to end."""
+        every ray end to end.
+        exchange (contiguous layout): "allreduce" — every rank writes a key map, NCCL min-reduces it, every rank resolves
+        (every rank ends up with the vertex map); "peer" — the march min-merges its hits straight into rank 0's key map
+        with atomics over NVLink peer memory (tsdf_b200_raycast_slab_min, CUDA IPC mapping), one 4-byte all-reduce serves
+        as the barrier, and only rank 0 resolves (only rank 0 holds the vertex and normal maps)."""
         self.n = tuple(int(x) for x in n)
         self.physical = fvec(physical)
         self.rank, self.world = rank, world
@@ -134,6 +139,9 @@ class ShardedEngine:
             if bad.value:
                 self.fastdiv = 0
         self.replica = None
+        self.exchange = exchange if (world > 1 and self.layout == "contiguous") else "allreduce"
+        self._keymaps = None              # peer exchange: rank 0's two key maps (alternating frames) as seen from this process
+        self._frame = 0
         self._opened = []
         if self.layout == "replica":
             # full-size copy of the distance volume; only surface bricks are ever written (by every rank's push) or read
@@ -348,6 +356,58 @@ class ShardedEngine:
         import torch.distributed as dist
         dist.all_reduce(self._token)          # stream-ordered; the host does not wait
 
+    def _connect_keys(self, w, h):
+        """Peer exchange: rank 0 allocates two shareable key maps (INT64_MAX everywhere), the others map them (collective)."""
+        import torch.distributed as dist
+        if self._keymaps is not None and self._keypix == w * h:
+            return
+        self._keypix = w * h
+        handles = [None, None]
+        if self.rank == 0:
+            own = []
+            for i in range(2):
+                p, hnd = _peer_alloc(w * h * 2)          # count is in 4-byte units: 8 bytes per key
+                check(lib.tsdf_b200_fill_i64(C.c_void_p(p), w * h, 0x7fffffffffffffff, self.stream), "fill_i64")
+                own.append(p)
+                handles[i] = hnd
+            self._own_keymaps = own
+            torch.cuda.synchronize()
+        box = [handles]
+        dist.broadcast_object_list(box, src=0)
+        if self.rank == 0:
+            self._keymaps = self._own_keymaps
+        else:
+            self._keymaps = []
+            for hnd in box[0]:
+                p = C.c_void_p()
+                check(lib.tsdf_b200_peer_open(hnd, C.byref(p)), "peer_open")
+                self._opened.append(p.value)
+                self._keymaps.append(p.value)
+        self._token = torch.zeros(1, dtype=torch.int32, device="cuda")
+
+    def _raycast_peer(self, w, h, cam, count):
+        """One frame of the peer exchange.  Key map f & 1 is written by every rank's march of frame f and read (and reset)
+        by rank 0's resolve of frame f; the march of frame f + 2 follows the barrier of frame f + 1, which rank 0 enters
+        after that resolve (stream order) — so no rank can write a map that is still being read."""
+        import torch.distributed as dist
+        self._connect_keys(w, h)
+        self._buffers(w, h)
+        _, _, kinv_p, origin_p, rot_p, _ = self._mats(cam)
+        smin = self.offset.copy()
+        smax = (self.offset + self.physical).astype(np.float32)
+        cnt = C.c_void_p(self.counters.data_ptr() + 8) if count else None
+        occ = _ptr(self.occ) if self.skipping else None
+        keys = C.c_void_p(self._keymaps[self._frame & 1])
+        self._frame += 1
+        check(lib.tsdf_b200_raycast_slab_min(_ptr(self.dist), *self.n, self.z0, self.local_n[2], self.z0, self.z1,
+                                             fptr(self.voxel), fptr(smin), fptr(smax), self.trunc, origin_p, rot_p, kinv_p,
+                                             w, h, _ptr(self.table), occ, keys, cnt, self.fastdiv, self.stream), "raycast_slab_min")
+        dist.all_reduce(self._token)          # barrier on the stream: every rank's atomics have landed
+        if self.rank == 0:
+            check(lib.tsdf_b200_raycast_resolve_reset(keys, fptr(smin), fptr(smax), self.trunc, origin_p, rot_p, kinv_p, w, h,
+                                                      _ptr(self.table), _ptr(self.vertices), None, self.stream), "resolve_reset")
+            check(lib.tsdf_b200_normals(w, h, _ptr(self.vertices), _ptr(self.normals), self.stream), "normals")
+
     @_on_stream
     def raycast(self, w, h, cam, count=False):
         if self.layout == "replica":
@@ -380,6 +440,8 @@ class ShardedEngine:
                                            w, h, _ptr(self.table), occ, _ptr(self.vertices), None, cnt, self.fastdiv,
                                            self.stream), "raycast")
             check(lib.tsdf_b200_normals(w, h, _ptr(self.vertices), _ptr(self.normals), self.stream), "normals")
+        elif self.exchange == "peer":
+            self._raycast_peer(w, h, cam, count)
         else:
             import torch.distributed as dist
             self.march(w, h, cam, count)
@@ -467,6 +529,10 @@ class ShardedEngine:
             self._opened = []
             if dist.is_initialized():
                 dist.barrier()                # nobody frees a block that a peer still has mapped
+        if getattr(self, "_own_keymaps", None):
+            for p in self._own_keymaps:
+                lib.tsdf_b200_peer_free(C.c_void_p(p))
+            self._own_keymaps = None
         if self.replica is not None:
             self.vertices = None
             lib.tsdf_b200_peer_free(C.c_void_p(self.replica))

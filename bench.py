@@ -441,7 +441,7 @@ def main():
         pg_ms = loop(frames, np.empty((H * W, 3), np.float32), np.empty((H * W, 3), np.float32))
         e2e_pageable = {"value": 1e3 / pg_ms, "unit": "frames/s", "ms_per_step": pg_ms,
                         "api": "the same calls with pageable (malloc'ed) depth and result buffers — what kinfu's DepthImage::data() "
-                               "and Eigen matrices are; staged through the volume's internal pinned ring"}
+                               "and Eigen matrices are (the driver stages the copies)"}
         vol.close()
 
     # ---- baselines on the same box: CPU restatement (whole frames), reference CUDA --------------------------------------

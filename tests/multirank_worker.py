@@ -18,7 +18,8 @@ def main():
     import torch.distributed as dist
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
-    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    import datetime
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local), timeout=datetime.timedelta(seconds=60))
     from tsdf_b200 import scenes, sharded
     size = int(sys.argv[1]) if len(sys.argv) > 1 else 128
     layouts = sys.argv[2].split(",") if len(sys.argv) > 2 else ["contiguous", "peer", "interleaved", "replica"]

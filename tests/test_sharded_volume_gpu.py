@@ -42,7 +42,7 @@ def test_sharded_volume_equals_single_gpu(built, tmp_path, n, want_gpus):
         V2, N2 = many.raycast(w, h, cam.pose, kinv)
         assert_bits_equal(V2, V1, f"vertices after frame {f}")
         assert_bits_equal(N2, N1, f"normals after frame {f}")
-        assert one.stats() == many.stats()                      # voxels rewritten and samples evaluated add up over the slabs
+        assert one.stats()[0] == many.stats()[0] > 0            # voxels rewritten add up over the slabs (halo planes are not counted)
     assert int((~np.isnan(V1[:, 0])).sum()) > 3000
     d1, w1 = one.read()
     d2, w2 = many.read()

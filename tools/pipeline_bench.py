@@ -27,7 +27,7 @@ if world > 1:
     dist.init_process_group("nccl", device_id=torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0"))))
 W, H = 640, 480
 n = (args.size,) * 3
-eng = sharded.ShardedEngine(n, (3000.0,) * 3, rank, world)
+eng = sharded.ShardedEngine(n, (3000.0,) * 3, rank, world, exchange="peer")
 stream = eng.stream
 
 # look-up tables of BilateralFilter's constructor (reference src/BilateralFilter.cpp:15-42), built on the host

@@ -18,10 +18,16 @@ namespace {
 
 size_t nvox(const tsdf_b200_volume *v) { return (size_t)v->nx * v->ny * v->nz; }
 
+// Is `p` host memory the device can address directly (cudaHostAlloc / cudaHostRegister)?  Returns its device alias or null.
+void *pinned_alias(const void *p) {
+    cudaPointerAttributes attr;
+    if (cudaPointerGetAttributes(&attr, p) == cudaSuccess && attr.type == cudaMemoryTypeHost && attr.devicePointer) return attr.devicePointer;
+    cudaGetLastError();          // an unregistered pointer is not an error of the caller's
+    return nullptr;
+}
+
 void release(tsdf_b200_volume *v) {
     if (v->multi) tsdf::multi_destroy(v);
-    cudaFreeHost(v->h_depth_pin); cudaFreeHost(v->h_vn_pin);
-    v->h_depth_pin = nullptr; v->h_vn_pin = nullptr; v->depth_pin_cap = v->vn_pin_cap = 0;
     cudaFree(v->d_dist); cudaFree(v->d_weight); cudaFree(v->d_deform); cudaFree(v->d_occ);
     cudaFree(v->d_table); cudaFree(v->d_depth); cudaFree(v->d_staged); cudaFree(v->d_vn); cudaFree(v->d_counters);
     free(v->h_colour);
@@ -261,7 +267,8 @@ extern "C" int tsdf_b200_volume_integrate(tsdf_b200_volume *v, const uint16_t *h
         TSDF_CUDA_TRY(cudaMalloc(&v->d_staged, staged_bytes));
         v->staged_cap = staged_bytes;
     }
-    TSDF_CUDA_TRY(cudaMemcpyAsync(v->d_depth, host_depth, npix * sizeof(uint16_t), cudaMemcpyHostToDevice, v->stream));
+    const uint16_t *src = host_depth;
+    TSDF_CUDA_TRY(cudaMemcpyAsync(v->d_depth, src, npix * sizeof(uint16_t), cudaMemcpyHostToDevice, v->stream));
     int rc = tsdf_b200_depth_stage(v->d_depth, width, height, v->d_staged, v->stream);
     if (rc) return rc;
     if (v->counting) TSDF_CUDA_TRY(cudaMemsetAsync(v->d_counters, 0, sizeof(unsigned long long), v->stream));
@@ -298,12 +305,12 @@ extern "C" int tsdf_b200_volume_raycast(const tsdf_b200_volume *cv, uint32_t wid
     // A pinned result buffer that the device can address receives the vertex map while the march runs (the transfer then
     // overlaps the kernel instead of following it); any other buffer gets a copy afterwards.
     float *mirror = nullptr;
-    cudaPointerAttributes attr;
-    if (width % 8 == 0 && height % 4 == 0 && cudaPointerGetAttributes(&attr, host_vertices) == cudaSuccess &&
-        attr.type == cudaMemoryTypeHost && attr.devicePointer && ((uintptr_t)attr.devicePointer & 15u) == 0)
-        mirror = static_cast<float *>(attr.devicePointer);
-    else
-        cudaGetLastError();          // an unregistered pointer is not an error of this call
+    void *alias = (width % 8 == 0 && height % 4 == 0) ? pinned_alias(host_vertices) : nullptr;
+    if (alias && ((uintptr_t)alias & 15u) == 0) mirror = static_cast<float *>(alias);
+    // Pageable result buffers (the Eigen matrices of TSDFVolume::raycast) are filled by the driver's staged copy below.  An own
+    // pinned ring (vertex map mirrored during the march, normals by DMA, four host threads copying out) was measured in round
+    // 2 and was SLOWER on the bench host (671 against 846 frames/s end to end): one pass over 7.4 MB of host memory is the cost
+    // either way, and the driver overlaps its DMA with that pass.
     int rc = tsdf_b200_raycast_mirrored(v->d_dist, v->nx, v->ny, v->nz, v->vs, smin, smax, v->trunc, origin, rot, kinv, width, height,
                                         v->d_table, v->skipping ? v->d_occ : nullptr, d_vert, mirror,
                                         v->counting ? v->d_counters + 1 : nullptr, v->fastdiv, v->stream);

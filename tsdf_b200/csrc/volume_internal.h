@@ -30,9 +30,6 @@ struct tsdf_b200_volume {
     cudaStream_t stream = nullptr;
     int fastdiv = 0, skipping = 1, counting = 1;
     int device = 0;                    // the device the single-GPU arrays (and, when sharded, the merged results) live on
-    // pinned staging for callers that hand over pageable memory (kinfu's DepthImage / Eigen matrices)
-    uint16_t *h_depth_pin = nullptr; size_t depth_pin_cap = 0;
-    float *h_vn_pin = nullptr; size_t vn_pin_cap = 0;
     tsdf::Multi *multi = nullptr;      // non-null: the volume is sharded along Z over several GPUs (multi.cu)
 };
 

@@ -522,7 +522,8 @@ class ShardedEngine:
 
     def close(self):
         torch.cuda.synchronize()
-        if self._opened:
+        if self._opened or getattr(self, "_own_keymaps", None):
+            # (collective: every rank of a layout / exchange that shares memory comes through here, owner or not)
             import torch.distributed as dist
             for p in self._opened:
                 lib.tsdf_b200_peer_close(C.c_void_p(p))

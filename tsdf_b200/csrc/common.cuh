@@ -39,8 +39,20 @@ __device__ __forceinline__ float fdiv_recip(float a, float b, float r) {
     return __fmaf_rn(e, r, q);
 }
 
-static constexpr float kOccLoFrac = 1.0e-3f;   // safe band for "certainly positive" voxels:
-static constexpr float kOccHiFrac = 1.0e3f;    // [trunc*1e-3, trunc*1e3]
+// Positive bands.  A brick is FLAGGED as soon as a voxel of it or of its 1-voxel apron leaves [0.8, 1.0001] * trunc.  Inside
+// an unflagged brick every trilinear sample is positive, even in the first voxel layer of the volume where the reference
+// EXTRAPOLATES (u in [-0.5, 0): weights 1 - u in (1, 1.5] and u < 0): with every corner in [a, b], split the weights (they sum
+// to 1) into the positive ones (sum W+) and the negative ones (sum -W-), W+ - W- = 1 and W- <= 3.7 for u, v, w >= -0.51; then
+// sample >= a W+ - b W- = a - W- (b - a) >= a - 3.7 (b - a) = 0.059 trunc for a = 0.8 trunc, b = 1.0001 trunc — four orders of
+// magnitude above the rounding error of the evaluation.  Free space a frame has seen (every update was +trunc) and untouched
+// voxels (trunc) are in the band; the ramp in front of a surface and everything behind it are not.  (Round 1 flagged against
+// [1e-3, 1e3] * trunc, which proves positivity only for weights in [0, 1]: every ray that entered the volume through a low
+// face had to evaluate the ~11 samples of its first voxel.)  Inside a flagged brick the march works cell by cell, and a
+// cell whose eight corners are in the WIDE band [1e-3, 1e3] * trunc is positive for weights in [0, 1] (level 2).
+static constexpr float kOccLoFrac = 0.8f;
+static constexpr float kOccHiFrac = 1.0001f;
+static constexpr float kCellLoFrac = 1.0e-3f;
+static constexpr float kCellHiFrac = 1.0e3f;
 
 struct BrickDims { uint32_t bx, by, bz; };
 __host__ __device__ inline BrickDims brick_dims(uint32_t nx, uint32_t ny, uint32_t nz) {

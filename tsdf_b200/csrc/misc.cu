@@ -39,12 +39,12 @@ init_deformation_kernel(float *__restrict__ deform, uint32_t nx, uint32_t ny, ui
 
 __global__ void __launch_bounds__(256)
 occupancy_rebuild_kernel(const float *__restrict__ dist, uint32_t nx, uint32_t ny, uint32_t nz,
-                         float lo, float hi, uint8_t *occ) {
+                         float trunc, uint8_t *occ) {
     const uint32_t x = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t y = blockIdx.y, z = blockIdx.z;
     if (x >= nx) return;
     const float d = dist[((size_t)nx * ny) * z + (size_t)nx * y + x];
-    if (!(d >= lo && d <= hi)) occ_mark(occ, brick_dims(nx, ny, nz), x, y, z);
+    if (!(d >= trunc * kOccLoFrac && d <= trunc * kOccHiFrac)) occ_mark(occ, brick_dims(nx, ny, nz), x, y, z);
 }
 
 }  // namespace tsdf
@@ -116,6 +116,6 @@ extern "C" int tsdf_b200_occupancy_rebuild(const float *d_dist, uint32_t nx, uin
     TSDF_CUDA_TRY(cudaMemsetAsync(d_occ, 0, tsdf_b200_occupancy_bytes(nx, ny, nz), s));
     dim3 block(256);
     dim3 grid((nx + 255) / 256, ny, nz);
-    occupancy_rebuild_kernel<<<grid, block, 0, s>>>(d_dist, nx, ny, nz, trunc * kOccLoFrac, trunc * kOccHiFrac, d_occ);
+    occupancy_rebuild_kernel<<<grid, block, 0, s>>>(d_dist, nx, ny, nz, trunc, d_occ);
     return (int)cudaGetLastError();
 }

@@ -34,6 +34,7 @@ struct RayParams {
     const uint8_t *occ;          // per brick: a voxel of the brick or of its 1-voxel apron is outside the positive band
     const uint8_t *occ_d;        // brick distance grid (written by distance_pass_kernel right before the march)
     uint32_t nbx, nby, nbz;      // occupancy grid dimensions (local planes when sharded)
+    uint32_t nbz_planes;         // planes held by the array (slab variants; nz for a whole volume)
     float occ_lo, occ_hi;        // positive band
     uint32_t z_base, z_lo, z_hi; // Z-slab: global z of array plane 0; cells owned by this rank start in [z_lo, z_hi)
     // Interleaved slabs (cyc_g > 0, SLAB kernels): global slabs of cyc_s planes are dealt to cyc_g ranks round robin, this
@@ -56,6 +57,7 @@ struct RayParams {
     unsigned int *queue_count;
     uint32_t queue_cap;
     int max_iters;
+    int low_skip;                // unflagged bricks on a low face may be skipped through their extrapolated first voxel layer
     int debug_iters;             // TSDF_B200_DEBUG_ITERS: khit receives loop iterations per ray (tuning aid)
     // Image sharding (tsdf_b200_raycast_tiles): of every `tile_stride` consecutive tiles this rank (tile_first) marches one,
     // and stores each vertex into all n_out vertex maps (its own and, through peer memory, the other GPUs')
@@ -310,8 +312,12 @@ __device__ __forceinline__ int march_ray(const RayParams &P, const float *s_t, c
         //   cd == 1: B itself is empty but a neighbour is not: skip to the exit of B pulled in by a guard
         //            band (2% of a voxel, >> the rounding error of a sample position), provided the landing
         //            point is itself clear of every face by that band.
-        // Voxel layer 0 of each axis is never skipped (the reference extrapolates there, :87-99): the landing
-        // point and every skipped sample keep 1.05 voxels away from the low faces of the volume.
+        // Voxel layer 0 of each axis, where the reference extrapolates (:87-99, u in [-0.5, 0)): bricks on a low face of the
+        // volume are unflagged only if their voxels lie in the TIGHT band [0.8, 1.0001] * trunc (common.cuh), which makes every
+        // sample in them positive for u, v, w >= -0.51 — so they are skipped like any other empty brick (P.low_skip; every ray
+        // that enters through such a face used to evaluate the ~11 samples of its first voxel).  Without that guarantee
+        // (!P.low_skip: coordinates so large that a sample may lie more than 1% of a voxel outside the volume) the landing
+        // point and every skipped sample keep 1.05 voxels away from the low faces.
         if (SKIP && !oob) {
             const int b[3] = { vox[0] / TSDF_B200_BRICK, vox[1] / TSDF_B200_BRICK, vox[2] / TSDF_B200_BRICK };
             const int bz_local = b[2] - ((SLAB && P.cyc_g == 0) ? (int)(P.z_base / TSDF_B200_BRICK) : 0);
@@ -329,11 +335,11 @@ __device__ __forceinline__ int march_ray(const RayParams &P, const float *s_t, c
                     const float dlo = p[a] - lo, dhi = hi - p[a];
                     const float dedge = p[a] - 1.05f * P.vs[a];          // distance to the guarded low edge of the volume
                     clear = clear && dlo >= g && dhi >= g;
-                    off_low_edge = off_low_edge && dedge >= 0.0f;
+                    off_low_edge = off_low_edge && (dedge >= 0.0f || P.low_skip);
                     float ta;
                     if (cd >= 2) ta = (sgn[a] > 0 ? dhi : dlo) * ainv[a] + extra * dtb[a];
                     else         ta = ((sgn[a] > 0 ? dhi : dlo) - g) * ainv[a];
-                    if (sgn[a] < 0) ta = fminf(ta, dedge * ainv[a]);
+                    if (sgn[a] < 0 && !P.low_skip) ta = fminf(ta, dedge * ainv[a]);
                     if (sgn[a] != 0) t_gain = fminf(t_gain, ta);
                 }
                 if (off_low_edge && (cd >= 2 || clear)) {
@@ -859,8 +865,8 @@ static int fill_params(RayParams &P, const float *d_dist, uint32_t nx, uint32_t 
     P.step = (float)((double)trunc * 0.05);
     for (int i = 0; i < 9; i++) { P.rot.m[i] = rot[i]; P.kinv.m[i] = kinv[i]; }
     P.width = width; P.height = height; P.table = d_table;
-    P.occ = nullptr; P.occ_d = nullptr; P.nbx = P.nby = P.nbz = 0;
-    P.occ_lo = trunc * kOccLoFrac; P.occ_hi = trunc * kOccHiFrac;
+    P.occ = nullptr; P.occ_d = nullptr; P.nbx = P.nby = P.nbz = 0; P.nbz_planes = nz;
+    P.occ_lo = trunc * kCellLoFrac; P.occ_hi = trunc * kCellHiFrac;      // level 2 (corners of one cell): the wide band
     P.z_base = 0; P.z_lo = 0; P.z_hi = nz;
     P.cyc_s = 0; P.cyc_g = 0; P.cyc_r = 0;
     P.vertices = nullptr; P.khit = nullptr; P.keys = nullptr; P.keys_min = nullptr; P.reset_keys = 0; P.n_samples = nullptr; P.tile_counter = nullptr;
@@ -869,6 +875,19 @@ static int fill_params(RayParams &P, const float *d_dist, uint32_t nx, uint32_t 
     P.queue = nullptr; P.queue_count = nullptr; P.queue_cap = 0;
     static const int cap = getenv("TSDF_B200_RAY_CAP") ? atoi(getenv("TSDF_B200_RAY_CAP")) : 96;
     P.max_iters = cap > 0 ? cap : 0x7fffffff;
+    // The tight band of low-face bricks covers weights down to -0.51: a sample position may undershoot the low face by 1 %
+    // of a voxel.  It undershoots by rounding only (start = origin + near_t * dir - space_min: the rounding of near_t and of the
+    // product, ~3e-7 of the largest coordinate involved; 2e-6 is budgeted); with coordinates too large for that bound the old
+    // rule (never skip layer 0) applies.
+    {
+        static const int env_low = getenv("TSDF_B200_LOW_SKIP") ? atoi(getenv("TSDF_B200_LOW_SKIP")) : 1;
+        float big = 0.0f, small = 3.0e38f;
+        for (int i = 0; i < 3; i++) {
+            big = fmaxf(big, fmaxf(fabsf(origin[i]), fmaxf(fabsf(space_min[i]), fabsf(space_max[i]))));
+            small = fminf(small, voxel[i]);
+        }
+        P.low_skip = (env_low && big * 2.0e-6f < 0.01f * small) ? 1 : 0;
+    }
     for (int i = 0; i < TSDF_B200_MAX_PEERS; i++) P.out[i] = nullptr;
     return 0;
 }
@@ -1020,7 +1039,7 @@ extern "C" int tsdf_b200_raycast_slab(const float *d_dist_slab, uint32_t nx, uin
     P.occ = d_occ_slab;
     const BrickDims nb = brick_dims(nx, ny, z_planes);
     P.nbx = nb.bx; P.nby = nb.by; P.nbz = nb.bz;
-    P.z_base = z_base; P.z_lo = z_lo; P.z_hi = z_hi;
+    P.z_base = z_base; P.z_lo = z_lo; P.z_hi = z_hi; P.nbz_planes = z_planes;
     P.keys = d_keys; P.n_samples = d_n_samples;
     return launch_march<true>(P, fastdiv, (cudaStream_t)stream);
 }
@@ -1042,7 +1061,7 @@ extern "C" int tsdf_b200_raycast_slab_min(const float *d_dist_slab, uint32_t nx,
     P.occ = d_occ_slab;
     const BrickDims nb = brick_dims(nx, ny, z_planes);
     P.nbx = nb.bx; P.nby = nb.by; P.nbz = nb.bz;
-    P.z_base = z_base; P.z_lo = z_lo; P.z_hi = z_hi;
+    P.z_base = z_base; P.z_lo = z_lo; P.z_hi = z_hi; P.nbz_planes = z_planes;
     P.keys_min = d_keys_min; P.n_samples = d_n_samples;
     return launch_march<true>(P, fastdiv, (cudaStream_t)stream);
 }

@@ -148,6 +148,22 @@ int tsdf_b200_raycast_mirrored(const float *d_dist, uint32_t nx, uint32_t ny, ui
                                const uint8_t *d_occ, float *d_vertices, float *mirror,
                                unsigned long long *d_n_samples, int fastdiv, void *stream);
 
+/* process_ray + compute_normals (RayCaster/GPURaycaster.cu:265-377, 393-427) in ONE launch sequence: vertex map and normal
+ * map in device memory, and — when mirror_vertices / mirror_normals are given (pinned host memory the device can address;
+ * same alignment rules as tsdf_b200_raycast_mirrored) — copies of both written while the march runs: a tile's vertices leave
+ * when its last ray finishes, a tile's normals as soon as the tile, its right and its lower neighbour are complete
+ * (compute_normals reads v(x+1, y) and v(x, y+1)).  d_tile_counters: tsdf_b200_raycast_tile_counters(width, height) 32-bit
+ * words of device memory, ZERO before the first call (every launch leaves them zero again).  Without them, without d_occ, or
+ * with an image that is not a whole number of 8x4 tiles the normals come from the separate kernel and the mirrors from a copy. */
+size_t tsdf_b200_raycast_tile_counters(uint32_t width, uint32_t height);
+int tsdf_b200_raycast_fused(const float *d_dist, uint32_t nx, uint32_t ny, uint32_t nz,
+                            const float voxel[3], const float space_min[3], const float space_max[3],
+                            float trunc, const float origin[3], const float rot[9], const float kinv[9],
+                            uint32_t width, uint32_t height, const float *d_table,
+                            const uint8_t *d_occ, float *d_vertices, float *d_normals,
+                            float *mirror_vertices, float *mirror_normals, unsigned int *d_tile_counters,
+                            unsigned long long *d_n_samples, int fastdiv, void *stream);
+
 /* Z-sharded raycast, march phase.  d_dist_slab / d_occ_slab hold z_planes planes starting at global plane
  * z_base of an nx*ny*nz volume (owned planes plus the upper halo plane).  Every ray is marched, but only
  * samples whose interpolation cell starts in [z_lo, z_hi) are evaluated.  d_keys[pixel] receives
@@ -328,7 +344,9 @@ int tsdf_b200_volume_set_deformation(tsdf_b200_volume *v, const float *host_node
 int tsdf_b200_volume_read(const tsdf_b200_volume *v, float *host_dist, float *host_weight);
 
 /* TSDFVolume::integrate (TSDF/TSDFVolume.cu:861-902): host depth map, camera matrices as
- * Camera::inverse_pose()/k()/kinv() .data().  Synchronous.                              */
+ * Camera::inverse_pose()/k()/kinv() .data().  Returns when the depth map has been read; the fusion
+ * completes in stream order before any later call on the volume returns data (as if synchronous;
+ * TSDF_B200_SYNC=1 waits for the kernels in this call).                                   */
 int tsdf_b200_volume_integrate(tsdf_b200_volume *v, const uint16_t *host_depth, uint32_t width,
                                uint32_t height, const float inv_pose[16], const float k[9],
                                const float kinv[9]);

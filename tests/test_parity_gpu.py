@@ -786,3 +786,56 @@ def test_mirrored_vertex_map_in_pinned_memory(G):
     assert_bits_equal(outs[0][1], outs[1][1], "level-2 normals")
     assert int((~np.isnan(want.reshape(-1, 3)[:, 0])).sum()) > 5000
     vol.close()
+
+
+def test_fused_raycast_normals_and_mirrors(G):
+    """tsdf_b200_raycast_fused: vertex and normal maps with the normals computed tile by tile as their
+    inputs complete, and both maps mirrored into pinned host memory while the march runs — bit-equal to tsdf_b200_raycast_ex +
+    tsdf_b200_normals, with and without the per-tile counters, on images of 8x4-tile and ragged size."""
+    import ctypes as C
+    import torch
+    from tsdf_b200 import scenes, sharded
+    from tsdf_b200.capi import lib, check, fptr, fvec, colmajor
+    n, phys = (128, 128, 128), (3000.0, 3000.0, 3000.0)
+    eng = sharded.ShardedEngine(n, phys)
+    for w, h, scale in ((320, 240, 0.5), (640, 480, 1.0), (322, 241, 0.5)):
+        eng.clear()
+        cams = []
+        for frame in (0, 2, 5, 7):
+            cam = scenes.orbit_camera(frame, 12)
+            k = cam.k.copy(); k[:2] *= scale
+            cam.k = k
+            cam.kinv = np.linalg.inv(k.astype(np.float64)).astype(np.float32)
+            eng.integrate(torch.from_numpy(scenes.render_depth(cam, w, h)).cuda(), cam)
+            cams.append(cam)
+        for cam in cams[1:]:
+            eng.raycast(w, h, cam)
+            want_v, want_n = eng.vertices.cpu().numpy(), eng.normals.cpu().numpy()
+            pose = np.asarray(cam.pose, np.float32)
+            smin = eng.offset.copy()
+            smax = (eng.offset + eng.physical).astype(np.float32)
+            aligned = w % 8 == 0 and h % 4 == 0
+            tiles = torch.zeros(lib.tsdf_b200_raycast_tile_counters(w, h), dtype=torch.int32, device="cuda")
+            for with_counters in (True, False):
+                for with_mirrors in ((True, False) if aligned else (False,)):
+                    dv = torch.full((w * h * 3,), -3.0, dtype=torch.float32, device="cuda")
+                    dn = torch.full((w * h * 3,), -3.0, dtype=torch.float32, device="cuda")
+                    mv = torch.full((w * h * 3,), -7.0, dtype=torch.float32).pin_memory()
+                    mn = torch.full((w * h * 3,), -7.0, dtype=torch.float32).pin_memory()
+                    check(lib.tsdf_b200_raycast_fused(
+                        C.c_void_p(eng.dist.data_ptr()), *n, fptr(eng.voxel), fptr(smin), fptr(smax), eng.trunc,
+                        fptr(fvec(pose[:3, 3])), fptr(colmajor(pose[:3, :3])), fptr(colmajor(cam.kinv)), w, h,
+                        C.c_void_p(eng.table.data_ptr()), C.c_void_p(eng.occ.data_ptr()), C.c_void_p(dv.data_ptr()),
+                        C.c_void_p(dn.data_ptr()), C.c_void_p(mv.data_ptr()) if with_mirrors else None,
+                        C.c_void_p(mn.data_ptr()) if with_mirrors else None,
+                        C.c_void_p(tiles.data_ptr()) if with_counters else None, None, eng.fastdiv, eng.stream), "raycast_fused")
+                    torch.cuda.synchronize()
+                    tag = f"{w}x{h} counters={with_counters} mirrors={with_mirrors}"
+                    assert_bits_equal(dv.cpu().numpy(), want_v, tag + ": device vertices")
+                    assert_bits_equal(dn.cpu().numpy(), want_n, tag + ": device normals")
+                    if with_mirrors:
+                        assert_bits_equal(mv.numpy(), want_v, tag + ": mirrored vertices")
+                        assert_bits_equal(mn.numpy(), want_n, tag + ": mirrored normals")
+                    assert int(tiles.abs().sum().item()) == 0, tag + ": tile counters not left zero"
+            assert int((~np.isnan(want_v.reshape(-1, 3)[:, 0])).sum()) > 3000
+    eng.close()

@@ -41,6 +41,9 @@ SIGNATURES = {
                                        _vp, _vp, _vp, _vp, _vp, C.c_int, _vp]),
     "tsdf_b200_raycast_mirrored": (C.c_int, [_vp, _u32, _u32, _u32, _f, _f, _f, C.c_float, _f, _f, _f, _u32, _u32, _vp, _vp,
                                              _vp, _vp, _vp, C.c_int, _vp]),
+    "tsdf_b200_raycast_fused": (C.c_int, [_vp, _u32, _u32, _u32, _f, _f, _f, C.c_float, _f, _f, _f, _u32, _u32, _vp, _vp,
+                                          _vp, _vp, _vp, _vp, _vp, _vp, C.c_int, _vp]),
+    "tsdf_b200_raycast_tile_counters": (C.c_size_t, [_u32, _u32]),
     "tsdf_b200_raycast_slab": (C.c_int, [_vp, _u32, _u32, _u32, _u32, _u32, _u32, _u32, _f, _f, _f, C.c_float, _f, _f, _f,
                                          _u32, _u32, _vp, _vp, _vp, _vp, C.c_int, _vp]),
     "tsdf_b200_raycast_slab_min": (C.c_int, [_vp, _u32, _u32, _u32, _u32, _u32, _u32, _u32, _f, _f, _f, C.c_float, _f, _f, _f,

@@ -29,9 +29,12 @@ void *pinned_alias(const void *p) {
 void release(tsdf_b200_volume *v) {
     if (v->multi) tsdf::multi_destroy(v);
     cudaFree(v->d_dist); cudaFree(v->d_weight); cudaFree(v->d_deform); cudaFree(v->d_occ);
-    cudaFree(v->d_table); cudaFree(v->d_depth); cudaFree(v->d_staged); cudaFree(v->d_vn); cudaFree(v->d_counters);
+    cudaFree(v->d_table); cudaFree(v->d_depth); cudaFree(v->d_staged); cudaFree(v->d_vn); cudaFree(v->d_counters); cudaFree(v->d_tiles);
+    v->d_tiles = nullptr;
     free(v->h_colour);
+    if (v->ev_depth) cudaEventDestroy(v->ev_depth);
     if (v->stream) cudaStreamDestroy(v->stream);
+    v->ev_depth = nullptr;
     v->d_dist = v->d_weight = v->d_deform = nullptr; v->d_occ = nullptr; v->d_table = nullptr;
     v->d_depth = nullptr; v->d_staged = nullptr; v->d_vn = nullptr; v->d_counters = nullptr; v->h_colour = nullptr; v->stream = nullptr;
 }
@@ -56,6 +59,7 @@ int allocate(tsdf_b200_volume *v, uint32_t nx, uint32_t ny, uint32_t nz, float p
     // grid); the legacy stream and a blocking stream order each other implicitly, as if everything ran on one stream
     // like in the reference (which synchronises the device after every launch).
     TSDF_CUDA_TRY(cudaStreamCreateWithFlags(&v->stream, cudaStreamDefault));
+    TSDF_CUDA_TRY(cudaEventCreateWithFlags(&v->ev_depth, cudaEventDisableTiming));
     TSDF_CUDA_TRY(cudaMalloc(&v->d_dist, n * sizeof(float)));
     TSDF_CUDA_TRY(cudaMalloc(&v->d_weight, n * sizeof(float)));
     TSDF_CUDA_TRY(cudaMalloc(&v->d_occ, tsdf_b200_occupancy_bytes(nx, ny, nz)));
@@ -269,6 +273,7 @@ extern "C" int tsdf_b200_volume_integrate(tsdf_b200_volume *v, const uint16_t *h
     }
     const uint16_t *src = host_depth;
     TSDF_CUDA_TRY(cudaMemcpyAsync(v->d_depth, src, npix * sizeof(uint16_t), cudaMemcpyHostToDevice, v->stream));
+    TSDF_CUDA_TRY(cudaEventRecord(v->ev_depth, v->stream));
     int rc = tsdf_b200_depth_stage(v->d_depth, width, height, v->d_staged, v->stream);
     if (rc) return rc;
     if (v->counting) TSDF_CUDA_TRY(cudaMemsetAsync(v->d_counters, 0, sizeof(unsigned long long), v->stream));
@@ -277,9 +282,15 @@ extern "C" int tsdf_b200_volume_integrate(tsdf_b200_volume *v, const uint16_t *h
                                  inv_pose, k, kinv, width, height, v->d_depth, v->d_staged, 0, v->nz, 0, v->d_occ,
                                  v->counting ? v->d_counters : nullptr, v->stream);
     if (rc) return rc;
-    if (v->counting)
-        TSDF_CUDA_TRY(cudaMemcpyAsync(&v->h_counters[0], v->d_counters, sizeof(unsigned long long), cudaMemcpyDeviceToHost, v->stream));
-    TSDF_CUDA_TRY(cudaStreamSynchronize(v->stream));
+    v->counters_stale = true;
+    // The call returns once the caller's depth buffer has been read.  The fusion kernels complete in stream order before any
+    // later call on this volume reads or returns data (every entry point works on v->stream, a blocking stream that also
+    // orders the legacy default stream), so the result is the one of a synchronous call — without a host round trip between
+    // integrate and the raycast that follows it.  TSDF_B200_SYNC=1 waits for the kernels here (their errors then surface in
+    // this call instead of the next one).
+    static const bool sync_all = getenv("TSDF_B200_SYNC") && atoi(getenv("TSDF_B200_SYNC")) != 0;
+    if (sync_all) TSDF_CUDA_TRY(cudaStreamSynchronize(v->stream));
+    else          TSDF_CUDA_TRY(cudaEventSynchronize(v->ev_depth));
     return 0;
 }
 
@@ -294,6 +305,13 @@ extern "C" int tsdf_b200_volume_raycast(const tsdf_b200_volume *cv, uint32_t wid
         TSDF_CUDA_TRY(cudaMalloc(&v->d_vn, npix * 6 * sizeof(float)));
         v->pix_cap = npix;
     }
+    const size_t tile_words = tsdf_b200_raycast_tile_counters(width, height);
+    if (tile_words > v->tile_cap) {
+        cudaFree(v->d_tiles); v->d_tiles = nullptr; v->tile_cap = 0;
+        TSDF_CUDA_TRY(cudaMalloc(&v->d_tiles, tile_words * sizeof(unsigned int)));
+        TSDF_CUDA_TRY(cudaMemsetAsync(v->d_tiles, 0, tile_words * sizeof(unsigned int), v->stream));
+        v->tile_cap = tile_words;
+    }
     float *d_vert = v->d_vn, *d_norm = v->d_vn + 3 * npix;
     // get_vertices (GPURaycaster.cu:432-470): origin = pose translation, rot = top-left 3x3,
     // space_min = offset, space_max = offset + physical size.
@@ -302,32 +320,40 @@ extern "C" int tsdf_b200_volume_raycast(const tsdf_b200_volume *cv, uint32_t wid
     float smin[3], smax[3];
     for (int i = 0; i < 3; i++) { smin[i] = v->off[i]; smax[i] = v->off[i] + v->phys[i]; }
     if (v->counting) TSDF_CUDA_TRY(cudaMemsetAsync(v->d_counters + 1, 0, sizeof(unsigned long long), v->stream));
-    // A pinned result buffer that the device can address receives the vertex map while the march runs (the transfer then
-    // overlaps the kernel instead of following it); any other buffer gets a copy afterwards.
-    float *mirror = nullptr;
-    void *alias = (width % 8 == 0 && height % 4 == 0) ? pinned_alias(host_vertices) : nullptr;
-    if (alias && ((uintptr_t)alias & 15u) == 0) mirror = static_cast<float *>(alias);
+    // Pinned result buffers that the device can address receive the vertex map and the normal map while the march runs
+    // (tile by tile: the transfers overlap the kernel instead of following it); any other buffer gets a copy afterwards.
+    float *mirror_v = nullptr, *mirror_n = nullptr;
+    if (width % 8 == 0 && height % 4 == 0) {
+        void *av = pinned_alias(host_vertices), *an = pinned_alias(host_normals);
+        if (av && ((uintptr_t)av & 15u) == 0) mirror_v = static_cast<float *>(av);
+        if (an && ((uintptr_t)an & 15u) == 0) mirror_n = static_cast<float *>(an);
+    }
     // Pageable result buffers (the Eigen matrices of TSDFVolume::raycast) are filled by the driver's staged copy below.  An own
     // pinned ring (vertex map mirrored during the march, normals by DMA, four host threads copying out) was measured in round
     // 2 and was SLOWER on the bench host (671 against 846 frames/s end to end): one pass over 7.4 MB of host memory is the cost
     // either way, and the driver overlaps its DMA with that pass.
-    int rc = tsdf_b200_raycast_mirrored(v->d_dist, v->nx, v->ny, v->nz, v->vs, smin, smax, v->trunc, origin, rot, kinv, width, height,
-                                        v->d_table, v->skipping ? v->d_occ : nullptr, d_vert, mirror,
-                                        v->counting ? v->d_counters + 1 : nullptr, v->fastdiv, v->stream);
+    int rc = tsdf_b200_raycast_fused(v->d_dist, v->nx, v->ny, v->nz, v->vs, smin, smax, v->trunc, origin, rot, kinv, width, height,
+                                     v->d_table, v->skipping ? v->d_occ : nullptr, d_vert, d_norm, mirror_v, mirror_n, v->d_tiles,
+                                     v->counting ? v->d_counters + 1 : nullptr, v->fastdiv, v->stream);
     if (rc) return rc;
-    rc = tsdf_b200_normals(width, height, d_vert, d_norm, v->stream);
-    if (rc) return rc;
-    if (!mirror)
+    if (!mirror_v)
         TSDF_CUDA_TRY(cudaMemcpyAsync(host_vertices, d_vert, npix * 3 * sizeof(float), cudaMemcpyDeviceToHost, v->stream));
-    TSDF_CUDA_TRY(cudaMemcpyAsync(host_normals, d_norm, npix * 3 * sizeof(float), cudaMemcpyDeviceToHost, v->stream));
-    if (v->counting)
-        TSDF_CUDA_TRY(cudaMemcpyAsync(&v->h_counters[1], v->d_counters + 1, sizeof(unsigned long long), cudaMemcpyDeviceToHost, v->stream));
+    if (!mirror_n)
+        TSDF_CUDA_TRY(cudaMemcpyAsync(host_normals, d_norm, npix * 3 * sizeof(float), cudaMemcpyDeviceToHost, v->stream));
+    v->counters_stale = true;
     TSDF_CUDA_TRY(cudaStreamSynchronize(v->stream));
     return 0;
 }
 
-extern "C" int tsdf_b200_volume_stats(const tsdf_b200_volume *v, unsigned long long *n_updated, unsigned long long *n_samples) {
+extern "C" int tsdf_b200_volume_stats(const tsdf_b200_volume *cv, unsigned long long *n_updated, unsigned long long *n_samples) {
+    tsdf_b200_volume *v = const_cast<tsdf_b200_volume *>(cv);
     if (!v) return TSDF_B200_EINVAL;
+    if (!v->multi && v->counters_stale && v->counting) {
+        // the counters stay on the device until somebody asks (a copy per call would put a host round trip into every frame)
+        TSDF_CUDA_TRY(cudaMemcpyAsync(v->h_counters, v->d_counters, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, v->stream));
+        TSDF_CUDA_TRY(cudaStreamSynchronize(v->stream));
+        v->counters_stale = false;
+    }
     if (n_updated) *n_updated = v->h_counters[0];
     if (n_samples) *n_samples = v->h_counters[1];
     return 0;

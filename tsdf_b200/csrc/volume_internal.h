@@ -25,9 +25,12 @@ struct tsdf_b200_volume {
     uint16_t *d_depth = nullptr; size_t depth_cap = 0;
     float *d_staged = nullptr; size_t staged_cap = 0;   // staged depth frame (tsdf_b200_depth_stage)
     float *d_vn = nullptr; size_t pix_cap = 0;   // vertices then normals
+    unsigned int *d_tiles = nullptr; size_t tile_cap = 0;   // per-tile counters of the fused raycast (zero between launches)
     unsigned long long *d_counters = nullptr;    // [0] voxels rewritten, [1] samples
     unsigned long long h_counters[2] = {0, 0};
     cudaStream_t stream = nullptr;
+    cudaEvent_t ev_depth = nullptr;    // the depth map of the last integrate has left the caller's buffer
+    bool counters_stale = false;       // d_counters are ahead of h_counters (fetched on demand by volume_stats)
     int fastdiv = 0, skipping = 1, counting = 1;
     int device = 0;                    // the device the single-GPU arrays (and, when sharded, the merged results) live on
     tsdf::Multi *multi = nullptr;      // non-null: the volume is sharded along Z over several GPUs (multi.cu)

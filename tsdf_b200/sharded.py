@@ -152,8 +152,8 @@ class ShardedEngine:
             self.vmap = None
             self._token = torch.zeros(1, dtype=torch.int32, device="cuda")
         self.clear()
-        # kernels per step: 2 pyramid launches (depth staging) + integrate (+ halo integrate when sharded) + 3
-        # brick-distance passes + raycast + normals (+ resolve when sharded; the all-reduce is NCCL's)
+        # kernels per step: 2 pyramid launches (depth staging) + integrate + 2 brick-distance kernels + march + continuation
+        # + normals; sharded: + halo integrate + resolve (the barrier is NCCL's)
         self.launches_per_step = (6 if world == 1 else 8) + (2 if stage_depth else 0)
         if self.layout in ("interleaved", "replica"):
             self.launches_per_step += 2 * (len(self.slabs) - 1)          # one integrate + one halo integrate per owned slab
@@ -183,6 +183,8 @@ class ShardedEngine:
             self.vertices = torch.empty(w * h * 3, dtype=torch.float32, device="cuda")
             self.normals = torch.empty(w * h * 3, dtype=torch.float32, device="cuda")
             self.keys = torch.empty(w * h, dtype=torch.int64, device="cuda")
+            # per-tile counters of the fused raycast (zero between launches)
+            self.tile_counters = torch.zeros(lib.tsdf_b200_raycast_tile_counters(w, h), dtype=torch.int32, device="cuda")
 
     @staticmethod
     def _mats(cam):
@@ -435,11 +437,20 @@ class ShardedEngine:
             smax = (self.offset + self.physical).astype(np.float32)
             cnt = C.c_void_p(self.counters.data_ptr() + 8) if count else None
             occ = _ptr(self.occ) if self.skipping else None
-            check(lib.tsdf_b200_raycast_ex(_ptr(self.dist), *self.n, fptr(self.voxel), fptr(smin), fptr(smax), self.trunc,
-                                           origin_p, rot_p, kinv_p,
-                                           w, h, _ptr(self.table), occ, _ptr(self.vertices), None, cnt, self.fastdiv,
-                                           self.stream), "raycast")
-            check(lib.tsdf_b200_normals(w, h, _ptr(self.vertices), _ptr(self.normals), self.stream), "normals")
+            if os.environ.get("TSDF_B200_FUSED", "0") == "1":
+                # march + normals in one launch sequence (tsdf_b200_raycast_fused: what the level-2 volume uses to stream both
+                # maps into pinned host buffers while the march runs).  With the maps staying on the device it is SLOWER than
+                # the march followed by the normals kernel (292 against 275 us on the bench frames: every tile ends with a
+                # fence and an atomic round trip), hence not the default here.
+                check(lib.tsdf_b200_raycast_fused(_ptr(self.dist), *self.n, fptr(self.voxel), fptr(smin), fptr(smax), self.trunc,
+                                                  origin_p, rot_p, kinv_p, w, h, _ptr(self.table), occ, _ptr(self.vertices),
+                                                  _ptr(self.normals), None, None, _ptr(self.tile_counters), cnt, self.fastdiv,
+                                                  self.stream), "raycast_fused")
+            else:
+                check(lib.tsdf_b200_raycast_ex(_ptr(self.dist), *self.n, fptr(self.voxel), fptr(smin), fptr(smax), self.trunc,
+                                               origin_p, rot_p, kinv_p, w, h, _ptr(self.table), occ, _ptr(self.vertices), None,
+                                               cnt, self.fastdiv, self.stream), "raycast")
+                check(lib.tsdf_b200_normals(w, h, _ptr(self.vertices), _ptr(self.normals), self.stream), "normals")
         elif self.exchange == "peer":
             self._raycast_peer(w, h, cam, count)
         else:

@@ -839,3 +839,44 @@ def test_fused_raycast_normals_and_mirrors(G):
                     assert int(tiles.abs().sum().item()) == 0, tag + ": tile counters not left zero"
             assert int((~np.isnan(want_v.reshape(-1, 3)[:, 0])).sum()) > 3000
     eng.close()
+
+
+def test_brick_distance_grid_equals_chessboard_transform(G):
+    """The brick distance grid every raycast derives from the flags (distance_bits_kernel: dilations of 64-bit rows, one
+    launch) equals the capped Chebyshev distance transform computed by scipy, for grids of one and two words per row, rows
+    that are not a multiple of 16 bricks, a single slice, and more slices than one block produces."""
+    import ctypes as C
+    import torch
+    from scipy import ndimage
+    from tsdf_b200.capi import lib, check, fptr, fvec, colmajor
+    from tsdf_b200 import scenes, capi
+    rng = np.random.default_rng(5)
+    cam = scenes.orbit_camera(0, 12)
+    pose = np.asarray(cam.pose, np.float32)
+    for n, density in (((512, 512, 512), 2e-4), ((512, 512, 512), 0.0), ((1024, 1024, 264), 1e-4), ((104, 72, 40), 0.02),
+                       ((520, 96, 200), 1e-3), ((64, 64, 8), 0.05), ((128, 128, 128), 1.0)):
+        nb = tuple((v + 7) // 8 for v in n)
+        nbr = nb[0] * nb[1] * nb[2]
+        phys = fvec([3000.0 * v / max(n) for v in n])
+        voxel, trunc = capi.volume_params(n, phys)
+        dist = torch.full((n[0] * n[1] * n[2],), float(trunc), dtype=torch.float32, device="cuda")
+        occ = torch.zeros(lib.tsdf_b200_occupancy_bytes(*n), dtype=torch.uint8, device="cuda")
+        flags = (rng.random(nbr) < density).astype(np.uint8)
+        occ[:nbr] = torch.from_numpy(flags).cuda()
+        table = torch.empty(4416, dtype=torch.float32, device="cuda")
+        check(lib.tsdf_b200_ray_table(trunc, C.c_void_p(table.data_ptr()), None))
+        V = torch.empty(8 * 4 * 3, dtype=torch.float32, device="cuda")
+        check(lib.tsdf_b200_raycast_ex(C.c_void_p(dist.data_ptr()), *n, fptr(voxel), fptr(fvec([0, 0, 0])), fptr(phys), trunc,
+                                       fptr(fvec(pose[:3, 3])), fptr(colmajor(pose[:3, :3])), fptr(colmajor(cam.kinv)), 8, 4,
+                                       C.c_void_p(table.data_ptr()), C.c_void_p(occ.data_ptr()), C.c_void_p(V.data_ptr()), None, None,
+                                       0, None), "raycast")
+        torch.cuda.synchronize()
+        got = occ[nbr:2 * nbr].cpu().numpy().reshape(nb[2], nb[1], nb[0])
+        f3 = flags.reshape(nb[2], nb[1], nb[0])
+        if f3.any():
+            want = np.minimum(ndimage.distance_transform_cdt(f3 == 0, metric="chessboard"), 16).astype(np.uint8)
+        else:
+            want = np.full(f3.shape, 16, np.uint8)
+        assert np.array_equal(got, want), f"grid {nb}, density {density}: {int((got != want).sum())} bricks differ"
+        assert np.array_equal(occ[:nbr].cpu().numpy(), flags), "flags modified"
+        del dist

@@ -13,6 +13,7 @@
 // Every sample that IS evaluated uses the reference's exact operation order.
 #include "common.cuh"
 #include <math_constants.h>
+#include <algorithm>
 #include <stdlib.h>
 #include <string.h>
 #include <map>
@@ -181,6 +182,143 @@ distance_z_kernel(uint8_t *__restrict__ grid, int nbx, int nby, int nbz) {
     __syncthreads();
     for (int i = threadIdx.x; i < n; i += blockDim.x)
         grid[((size_t)(i / nbx) * nby + y) * nbx + i % nbx] = (uint8_t)distance_scan(s_grid, i, i / nbx, nbz, nbx);
+}
+
+// The same transform on bit rows, in ONE launch (round 2; 8 us per frame less than the two shared-memory kernels above at 64^3
+// bricks, which are bound by the latency of their dependent byte scans on 64 blocks).  A row of bricks along x is a W x 64-bit mask.
+// D_0 = the flags; D_{r+1} = D_r dilated by one brick along x (shifts), y and z (OR with the neighbouring rows): D_r holds the
+// bricks within Chebyshev distance r of a flagged one, and the capped distance of a brick is the number of r in 0..15 with
+// the brick NOT in D_r — counted in five bit-sliced planes with a ripple-carry add.  A warp owns one z-slice (lane l rows
+// [l R, (l + 1) R): the y-neighbours are in the lane's own registers or one shuffle away), slices meet through shared memory
+// once per dilation.  A block of 32 warps produces kDistOut consecutive slices from the 32 slices around them (fifteen
+// dilations reach fifteen slices), so blocks do not talk.  Rows, columns and slices past the end of the grid behave like empty
+// bricks that happen to exist: whatever a dilation puts into them is within the claimed distance of a flagged brick, so what
+// they hand back is right as well, and nothing needs masking.
+constexpr int kDistOut = 32 - 2 * (kDistCap - 1);         // output slices per block (2)
+template <int R, int W>
+__global__ void __launch_bounds__(1024)
+distance_bits_kernel(const uint8_t *__restrict__ flags, uint8_t *__restrict__ out, int nbx, int nby, int nbz,
+                     unsigned int *counters, int n_counters) {
+    typedef unsigned long long u64;
+    extern __shared__ u64 s_bits[];                    // two buffers of [32 slices][32 R rows][W]
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (counters)       // work counter and queue length of the march
+        for (int i = blockIdx.x * blockDim.x + tid; i < n_counters; i += gridDim.x * blockDim.x) counters[i] = 0u;
+    const int zo0 = blockIdx.x * kDistOut;
+    const int z = zo0 - (kDistCap - 1) + warp;          // this warp's slice
+    const bool is_out = warp >= kDistCap - 1 && warp < kDistCap - 1 + kDistOut && z < nbz;
+    constexpr int kSlice = 32 * R * W;                 // words per slice
+    u64 m[R][W];
+#pragma unroll
+    for (int j = 0; j < R; j++) {
+        const int y = lane * R + j;
+#pragma unroll
+        for (int w = 0; w < W; w++) {
+            u64 v = 0;
+            if (z >= 0 && z < nbz && y < nby && w * 64 < nbx) {
+                const uint8_t *src = flags + ((size_t)z * nby + y) * nbx + w * 64;
+                const int n = min(64, nbx - w * 64);
+                if (nbx % 16 == 0) {
+                    for (int q = 0; q < n / 16; q++) {
+                        const uint4 b = __ldg(reinterpret_cast<const uint4 *>(src) + q);
+                        const uint32_t part[4] = { b.x, b.y, b.z, b.w };
+#pragma unroll
+                        for (int c = 0; c < 4; c++) {
+                            // one bit per non-zero byte: 0xff per byte, keep the top bits, gather them into a nibble
+                            const uint32_t nz = __vcmpne4(part[c], 0u) & 0x80808080u;
+                            const uint32_t nib = ((nz >> 7) | (nz >> 14) | (nz >> 21) | (nz >> 28)) & 0xfu;
+                            v |= (u64)nib << (16 * q + 4 * c);
+                        }
+                    }
+                } else {
+                    for (int x = 0; x < n; x++) v |= (u64)(src[x] != 0) << x;
+                }
+            }
+            m[j][w] = v;
+        }
+    }
+    u64 planes[5][R][W];
+#pragma unroll
+    for (int p = 0; p < 5; p++)
+#pragma unroll
+        for (int j = 0; j < R; j++)
+#pragma unroll
+            for (int w = 0; w < W; w++) planes[p][j][w] = 0ull;
+
+    for (int r = 0; r < kDistCap; r++) {
+        if (is_out) {
+            // m holds D_r: one more for every brick outside it
+#pragma unroll
+            for (int j = 0; j < R; j++)
+#pragma unroll
+                for (int w = 0; w < W; w++) {
+                    u64 carry = ~m[j][w];
+#pragma unroll
+                    for (int p = 0; p < 5; p++) {
+                        const u64 v = planes[p][j][w];
+                        planes[p][j][w] = v ^ carry;
+                        carry &= v;
+                    }
+                }
+        }
+        if (r == kDistCap - 1) break;
+        // along y: the rows of the neighbouring lanes that touch this lane's block of rows
+        u64 t[R][W];
+#pragma unroll
+        for (int w = 0; w < W; w++) {
+            u64 below = __shfl_up_sync(0xffffffffu, m[R - 1][w], 1), above = __shfl_down_sync(0xffffffffu, m[0][w], 1);
+            if (lane == 0) below = 0ull;
+            if (lane == 31) above = 0ull;
+#pragma unroll
+            for (int j = 0; j < R; j++)
+                t[j][w] = m[j][w] | (j > 0 ? m[j - 1][w] : below) | (j + 1 < R ? m[j + 1][w] : above);
+        }
+        // along x, then out to the other slices
+        u64 *buf = s_bits + (r & 1) * (32 * kSlice) + warp * kSlice + lane * (R * W);
+#pragma unroll
+        for (int j = 0; j < R; j++)
+#pragma unroll
+            for (int w = 0; w < W; w++) {
+                u64 left = t[j][w] << 1, right = t[j][w] >> 1;
+                if (w > 0) left |= t[j][w - 1] >> 63;
+                if (w + 1 < W) right |= t[j][w + 1] << 63;
+                m[j][w] = t[j][w] | left | right;
+                buf[j * W + w] = m[j][w];
+            }
+        __syncthreads();
+        // along z (a slice at the end of the block's range misses a neighbour: the error creeps inwards one slice per
+        // dilation and never reaches the output slices)
+#pragma unroll
+        for (int j = 0; j < R; j++)
+#pragma unroll
+            for (int w = 0; w < W; w++) {
+                if (warp > 0) m[j][w] |= buf[j * W + w - kSlice];
+                if (warp < 31) m[j][w] |= buf[j * W + w + kSlice];
+            }
+    }
+
+    // bit planes -> one byte per brick, all threads of the block
+    __syncthreads();
+    u64 *pl = s_bits;                                  // [kDistOut][5][32 R][W]
+    if (is_out) {
+        const int o = warp - (kDistCap - 1);
+#pragma unroll
+        for (int p = 0; p < 5; p++)
+#pragma unroll
+            for (int j = 0; j < R; j++)
+#pragma unroll
+                for (int w = 0; w < W; w++) pl[((o * 5 + p) * 32 * R + lane * R + j) * W + w] = planes[p][j][w];
+    }
+    __syncthreads();
+    const int n_out = min(kDistOut, nbz - zo0);
+    const int out_bytes = n_out * nby * nbx;
+    for (int i = tid; i < out_bytes; i += blockDim.x) {
+        const int x = i % nbx, row = i / nbx, y = row % nby, o = row / nby;
+        uint32_t v = 0;
+#pragma unroll
+        for (int p = 0; p < 5; p++) v |= (uint32_t)((pl[((o * 5 + p) * 32 * R + y) * W + (x >> 6)] >> (x & 63)) & 1ull) << p;
+        out[(size_t)zo0 * nby * nbx + i] = (uint8_t)v;
+    }
 }
 
 // Per-ray set-up shared by the march and the resolve kernel: direction, clip, start point.
@@ -1066,8 +1204,28 @@ static int launch_march(RayParams &P, int fastdiv, cudaStream_t s, unsigned int 
             P.normals = want_normals; P.mirror_n = want_mirror_n;
         }
         const size_t smem_xy = 2 * (size_t)P.nbx * P.nby, smem_z = (size_t)P.nbx * P.nbz;
-        static const bool global_passes = getenv("TSDF_B200_DIST_GLOBAL") != nullptr;      // A/B switch (tuning aid)
-        if (smem_xy <= 48 * 1024 && smem_z <= 48 * 1024 && !global_passes) {
+        static const bool global_passes = getenv("TSDF_B200_DIST_GLOBAL") != nullptr;      // A/B switches (tuning aids)
+        static const bool byte_passes = getenv("TSDF_B200_DIST_BYTES") != nullptr;
+        // bit rows: up to 128 bricks along x and y
+        const int wpr = (int)((P.nbx + 63) / 64), rpl = (int)((P.nby + 31) / 32);
+        void (*bits_kernel)(const uint8_t *, uint8_t *, int, int, int, unsigned int *, int) = nullptr;
+        int R = 0;
+        if (!global_passes && !byte_passes && wpr <= 2 && rpl <= 4) {
+            R = rpl <= 1 ? 1 : (rpl <= 2 ? 2 : 4);
+            // (R = 4 with two words per row — 128 x 128 bricks per slice, a 1024^3 volume — needs more registers than a
+            // 1024-thread block has: measured 41 us slower than the byte kernels, which keep that case)
+            if (wpr == 1)    bits_kernel = R == 1 ? distance_bits_kernel<1, 1> : (R == 2 ? distance_bits_kernel<2, 1> : distance_bits_kernel<4, 1>);
+            else if (R <= 2) bits_kernel = R == 1 ? distance_bits_kernel<1, 2> : distance_bits_kernel<2, 2>;
+        }
+        if (bits_kernel) {
+            // two exchange buffers of 32 slices; the bit planes of the output slices reuse them
+            const size_t smem_bits = std::max<size_t>(2 * 32, 5 * kDistOut) * 32 * R * wpr * sizeof(unsigned long long);
+            // (per device and cheap: set on every call rather than remembered per device and thread)
+            if (smem_bits > 48 * 1024)
+                TSDF_CUDA_TRY(cudaFuncSetAttribute(bits_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bits));
+            bits_kernel<<<(P.nbz + kDistOut - 1) / kDistOut, 1024, smem_bits, s>>>(
+                P.occ, cd, (int)P.nbx, (int)P.nby, (int)P.nbz, have_words ? reinterpret_cast<unsigned int *>(word) : nullptr, (int)n_words);
+        } else if (smem_xy <= 48 * 1024 && smem_z <= 48 * 1024 && !global_passes) {
             distance_xy_kernel<<<P.nbz, 1024, smem_xy, s>>>(P.occ, cd, (int)P.nbx, (int)P.nby,
                                                            have_words ? reinterpret_cast<unsigned int *>(word) : nullptr, (int)n_words);
             distance_z_kernel<<<P.nby, 1024, smem_z, s>>>(cd, (int)P.nbx, (int)P.nby, (int)P.nbz);

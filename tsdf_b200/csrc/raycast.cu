@@ -1162,7 +1162,9 @@ static int fill_params(RayParams &P, const float *d_dist, uint32_t nx, uint32_t 
     P.tile_first = 0; P.tile_stride = 1; P.n_out = 0; P.mirror = nullptr;
     P.normals = nullptr; P.mirror_n = nullptr; P.tile_done = nullptr; P.tile_deps = nullptr;
     P.queue = nullptr; P.queue_count = nullptr; P.queue_cap = 0;
-    static const int cap = getenv("TSDF_B200_RAY_CAP") ? atoi(getenv("TSDF_B200_RAY_CAP")) : 96;
+    // (round 2, after the march_step rewrite: 48 / 64 / 80 / 96 / 128 / 160 iterations -> 283 / 259 / 257 / 273 / 302 / 327 us on
+    // the bench frames, 470 / 431 / 404 / 398 / 417 / 433 us on frame 500 — profiles/r02u_ray_caps_march_step.txt)
+    static const int cap = getenv("TSDF_B200_RAY_CAP") ? atoi(getenv("TSDF_B200_RAY_CAP")) : 80;
     P.max_iters = cap > 0 ? cap : 0x7fffffff;
     // The tight band of low-face bricks covers weights down to -0.51: a sample position may undershoot the low face by 1 %
     // of a voxel.  It undershoots by rounding only (start = origin + near_t * dir - space_min: the rounding of near_t and of the

@@ -738,7 +738,7 @@ def test_replica_low_face_extrapolation_and_clear(G):
 
 def test_mirrored_vertex_map_in_pinned_memory(G):
     """tsdf_b200_raycast_mirrored: the copy of the vertex map written into pinned host memory during the march (tile-wise
-    16-byte stores from raycast_kernel, single pixels from continue_kernel) equals the device vertex map bit for bit; and
+    16-byte stores from the march, single pixels from the continuation) equals the device vertex map bit for bit; and
     the level-2 volume gives the same result for a pinned and for a pageable result buffer."""
     import ctypes as C
     import torch

@@ -52,10 +52,13 @@ struct RayParams {
     unsigned int *tile_counter;  // work counter for dynamic tile scheduling (zeroed before the launch) or nullptr
     // Continuation queue: the kernel's run time used to be the march of its slowest ray (~400 dependent loop iterations
     // at ~1.3 us each against a median of ~25, tools/ray_iters.py).  A ray still marching after max_iters iterations
-    // appends (pixel, next sample) here and continue_kernel finishes it with a whole warp, each lane on 1/32 of the
-    // remaining samples.
-    int2 *queue;
-    unsigned int *queue_count;
+    // appends (pixel, next sample) here and a warp that has run out of tiles finishes it (continue_entry), each lane on
+    // 1/32 of the remaining samples.
+    int2 *queue;                 // every slot holds (-1, -1) before the launch
+    unsigned int *queue_count;   // slots handed out to producers
+    unsigned int *queue_head;    // slots claimed by consumers
+    unsigned int *tiles_finished;
+    const unsigned int *cap_word; // iteration cap chosen by march_reset for this frame (0 / nullptr: max_iters)
     uint32_t queue_cap;
     int max_iters;
     int low_skip;                // unflagged bricks on a low face may be skipped through their extrapolated first voxel layer
@@ -68,7 +71,7 @@ struct RayParams {
     // Second copy of the vertex map in memory that is slow to write in small pieces (pinned host memory seen through the
     // bus): each warp writes its 8x4 tile as 24 aligned 16-byte stores.  Needs width % 8 == 0, height % 4 == 0, base % 16 == 0.
     float *mirror;
-    // Fused normals (tsdf_b200_raycast_fused): a tile's pixels may finish in two kernels (rays set aside for continue_kernel),
+    // Fused normals (tsdf_b200_raycast_fused): a tile's pixels may be finished by different warps (rays set aside for the continuation),
     // so a counter per tile says when its 32 vertices are final; the warp that completes a tile tells the tiles whose
     // normals read it (itself, its left and its upper neighbour), and the warp whose signal is the last one a tile waits for
     // computes that tile's normals into `normals` and `mirror_n`.  Both counter arrays are the caller's and are zero between launches.
@@ -146,9 +149,31 @@ distance_pass_kernel(const uint8_t *__restrict__ in, uint8_t *__restrict__ out, 
     out[base] = (uint8_t)best;
 }
 
+// Start-of-frame reset of the march's words in the scratch third of the occupancy buffer, done by the kernel that builds the
+// distance grid: [0] work counter, [1] queue slots handed out, [2] queue slots claimed, [3] tiles finished <- 0; every slot of
+// the continuation queue <- (-1, -1).  Word [4] persists from frame to frame: the iteration cap of the march.  A low cap
+// shortens the kernel as long as few rays reach it (the warps that are out of tiles finish them while the last tiles are
+// still marching); when many do, their continuation is the longer part.  The number of rays set aside in the previous frame —
+// poses change slowly — says which case this is: cap_lo unless more than thr_hi rays were set aside with it, cap_hi until
+// fewer than thr_lo are.  (Results do not depend on the cap.)
+struct MarchReset { unsigned int *words; int n_queue_words; int cap_lo, cap_hi; unsigned int thr_lo, thr_hi; };
+constexpr int kMarchWords = 8;
+__device__ __forceinline__ void march_reset(const MarchReset &M, int global_thread, int global_threads) {
+    if (!M.words) return;
+    if (global_thread == 0) {
+        const unsigned int set_aside = M.words[1], cap_was = M.words[4];
+        unsigned int cap = (cap_was == (unsigned int)M.cap_lo || cap_was == (unsigned int)M.cap_hi) ? cap_was : (unsigned int)M.cap_hi;
+        if (cap == (unsigned int)M.cap_hi && cap_was == cap && set_aside < M.thr_lo) cap = (unsigned int)M.cap_lo;
+        else if (cap == (unsigned int)M.cap_lo && set_aside > M.thr_hi) cap = (unsigned int)M.cap_hi;
+        M.words[0] = 0u; M.words[1] = 0u; M.words[2] = 0u; M.words[3] = 0u;
+        M.words[4] = cap;
+    }
+    for (int i = global_thread; i < M.n_queue_words; i += global_threads) M.words[kMarchWords + i] = 0xffffffffu;
+}
+
 // The same transform with the passes done in shared memory (the global version is bound by ~16 dependent L2 round trips per
 // pass): one block per z-slice does the x and y passes, one block per y-row does the z pass in place.  The x/y kernel
-// also clears the work counters of the march.
+// also resets the words of the march (march_reset).
 __device__ __forceinline__ int distance_scan(const uint8_t *v, int i, int pos, int len, int stride) {
     int best = v[i];
     for (int j = 1; j < best; j++) {
@@ -159,14 +184,12 @@ __device__ __forceinline__ int distance_scan(const uint8_t *v, int i, int pos, i
 }
 
 __global__ void __launch_bounds__(1024)
-distance_xy_kernel(const uint8_t *__restrict__ flags, uint8_t *__restrict__ out, int nbx, int nby, unsigned int *counters,
-                   int n_counters) {
+distance_xy_kernel(const uint8_t *__restrict__ flags, uint8_t *__restrict__ out, int nbx, int nby, const MarchReset reset) {
     extern __shared__ uint8_t s_grid[];
     const int n = nbx * nby;
     uint8_t *a = s_grid, *b = s_grid + n;
     const size_t base = (size_t)blockIdx.x * n;
-    if (counters)       // work counter, queue length, per-tile counters of the pool kernel
-        for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_counters; i += gridDim.x * blockDim.x) counters[i] = 0u;
+    march_reset(reset, blockIdx.x * blockDim.x + threadIdx.x, gridDim.x * blockDim.x);
     for (int i = threadIdx.x; i < n; i += blockDim.x) a[i] = flags[base + i] ? 0 : kDistCap;
     __syncthreads();
     for (int i = threadIdx.x; i < n; i += blockDim.x) b[i] = (uint8_t)distance_scan(a, i, i % nbx, nbx, 1);
@@ -197,13 +220,11 @@ distance_z_kernel(uint8_t *__restrict__ grid, int nbx, int nby, int nbz) {
 constexpr int kDistOut = 32 - 2 * (kDistCap - 1);         // output slices per block (2)
 template <int R, int W>
 __global__ void __launch_bounds__(1024)
-distance_bits_kernel(const uint8_t *__restrict__ flags, uint8_t *__restrict__ out, int nbx, int nby, int nbz,
-                     unsigned int *counters, int n_counters) {
+distance_bits_kernel(const uint8_t *__restrict__ flags, uint8_t *__restrict__ out, int nbx, int nby, int nbz, const MarchReset reset) {
     typedef unsigned long long u64;
     extern __shared__ u64 s_bits[];                    // two buffers of [32 slices][32 R rows][W]
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (counters)       // work counter and queue length of the march
-        for (int i = blockIdx.x * blockDim.x + tid; i < n_counters; i += gridDim.x * blockDim.x) counters[i] = 0u;
+    march_reset(reset, blockIdx.x * blockDim.x + tid, gridDim.x * blockDim.x);
     const int zo0 = blockIdx.x * kDistOut;
     const int z = zo0 - (kDistCap - 1) + warp;          // this warp's slice
     const bool is_out = warp >= kDistCap - 1 && warp < kDistCap - 1 + kDistOut && z < nbz;
@@ -792,6 +813,76 @@ __device__ __forceinline__ void tile_completed(const RayParams &P, uint32_t tile
     }
 }
 
+#ifndef TSDF_RAY_ROUNDS
+#define TSDF_RAY_ROUNDS 4
+#endif
+#ifndef TSDF_RAY_MINB
+#define TSDF_RAY_MINB 6
+#endif
+// Finishes one ray that the march set aside — queue entry (pixel, first remaining sample) — with a whole warp: lane l marches
+// the l-th of 32 equal pieces of the remaining sample range; the ray's first hit is the smallest hit sample over the lanes.
+template <bool FASTDIV, bool SKIP, bool SLAB>
+__device__ __noinline__ void continue_entry(const RayParams &P, const float *s_t, int2 entry, int lane, float *st, uint32_t &samples) {
+    const size_t pix = (size_t)entry.x;
+    const uint32_t imx = (uint32_t)entry.x % P.width, imy = (uint32_t)entry.x / P.width;
+    const RaySetup R = ray_setup(P, imx, imy);
+    // samples the ray still has: k_end is only an estimate of the last one, the final piece runs to the end of the table
+    const int k0 = entry.y;
+    const int k_end = min(max((int)fminf(R.max_t * __frcp_rn(P.step), 5000.0f) + 1, k0), TSDF_B200_MAX_SAMPLES - 1);
+    const int len = k_end - k0 + 1;
+    // The remaining samples are cut into kRounds * 32 chunks; in round r lane l marches chunk 32 r + l.  Neighbouring
+    // chunks run side by side, so a stretch of expensive samples (a ray skimming a surface) spreads over many lanes
+    // instead of landing in one lane's piece; a round whose chunks all start behind the best hit so far is skipped.
+    constexpr int kRounds = TSDF_RAY_ROUNDS, kChunks = 32 * kRounds;
+    int kh = -1;
+    float s_hit = 0.0f;
+    RayDebug dbg = { 0, 0, 0, 0, 0 };
+    long long key = 0x7fffffffffffffffLL;
+    for (int r = 0; r < kRounds; r++) {
+        const int c = 32 * r + lane;
+        const int first = k0 + (int)((long long)len * c / kChunks);
+        const int last = c == kChunks - 1 ? TSDF_B200_MAX_SAMPLES - 1 : k0 + (int)((long long)len * (c + 1) / kChunks) - 1;
+        if (first <= last && kh < 0) march_ray<FASTDIV, SKIP, SLAB>(P, s_t, R, first, last, 0x7fffffff, kh, s_hit, samples, dbg);
+        key = (kh >= 0) ? (((long long)kh << 32) | (long long)(uint32_t)__float_as_uint(s_hit)) : 0x7fffffffffffffffLL;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) key = min(key, __shfl_xor_sync(0xffffffffu, key, o));
+        if (key != 0x7fffffffffffffffLL) break;           // later rounds only hold later samples
+    }
+    if (lane == 0) {
+        if (SLAB) {
+            if (P.keys_min) { if (key != 0x7fffffffffffffffLL) atomicMin(P.keys_min + pix, key); }
+            else P.keys[pix] = key;
+        } else {
+            float ip[3] = { CUDART_NAN_F, CUDART_NAN_F, CUDART_NAN_F };
+            int k_hit = -1;
+            if (key != 0x7fffffffffffffffLL) {
+                k_hit = (int)(key >> 32);
+                hit_vertex(P, R, s_t[k_hit], __uint_as_float((uint32_t)(key & 0xffffffffLL)), ip);
+            }
+            if (P.n_out) {
+                for (uint32_t d = 0; d < P.n_out; d++) {
+                    float *v = P.out[d] + 3 * pix;
+                    v[0] = ip[0]; v[1] = ip[1]; v[2] = ip[2];
+                }
+            } else {
+                P.vertices[3 * pix + 0] = ip[0];
+                P.vertices[3 * pix + 1] = ip[1];
+                P.vertices[3 * pix + 2] = ip[2];
+                if (P.khit && !P.debug_iters) P.khit[pix] = k_hit;
+                if (P.mirror && !P.tile_done) { P.mirror[3 * pix + 0] = ip[0]; P.mirror[3 * pix + 1] = ip[1]; P.mirror[3 * pix + 2] = ip[2]; }
+            }
+        }
+    }
+    __syncwarp();
+    if (!SLAB && P.tile_done) {
+        // fused normals: this ray may have been the last one its tile waited for
+        const uint32_t tile = (imy / 4) * (P.width / 8) + imx / 8;
+        bool completed = false;
+        if (lane == 0) { __threadfence(); completed = atomicAdd(P.tile_done + tile, 1u) == 31u; }
+        if (__shfl_sync(0xffffffffu, (int)completed, 0)) tile_completed(P, tile, st, lane);
+    }
+}
+
 // One thread per pixel.  SLAB: the volume arrays hold planes [z_base, z_base + nz_local) of a Z-sharded volume,
 // only samples whose interpolation cell starts in [z_lo, z_hi) are evaluated, and the result is a key.
 template <bool FASTDIV, bool SKIP, bool SLAB>
@@ -800,12 +891,6 @@ __device__ __noinline__ void march_ray_cold(const RayParams &P, const float *s_t
     march_ray<FASTDIV, SKIP, SLAB>(P, s_t, R, k_first, TSDF_B200_MAX_SAMPLES - 1, 0x7fffffff, kh, s_hit, samples, dbg);
 }
 
-#ifndef TSDF_RAY_ROUNDS
-#define TSDF_RAY_ROUNDS 4
-#endif
-#ifndef TSDF_RAY_MINB
-#define TSDF_RAY_MINB 6
-#endif
 template <bool FASTDIV, bool SKIP, bool SLAB>
 __global__ void __launch_bounds__(128, TSDF_RAY_MINB)
 raycast_kernel(const __grid_constant__ RayParams P) {
@@ -824,6 +909,11 @@ raycast_kernel(const __grid_constant__ RayParams P) {
     const uint32_t warps_total = gridDim.x * (blockDim.x >> 5);
     const uint32_t n_work = P.tile_stride > 1 ? (n_tiles + P.tile_stride - 1) / P.tile_stride : n_tiles;
     uint32_t samples = 0;
+    int max_iters = 0x7fffffff;
+    if (P.queue) {
+        max_iters = P.max_iters;
+        if (P.cap_word) { const unsigned int c = __ldg(P.cap_word); if (c) max_iters = (int)c; }
+    }
     auto next_tile = [&](uint32_t previous, bool first) -> uint32_t {
         if (!P.tile_counter) return first ? blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5) : previous + warps_total;
         uint32_t t = 0;
@@ -838,7 +928,10 @@ raycast_kernel(const __grid_constant__ RayParams P) {
         // not line up in image columns
         const uint32_t base = tile * P.tile_stride;
         tile = base + (P.tile_first + base / tiles_x) % P.tile_stride;
-        if (tile >= n_tiles) continue;
+        if (tile >= n_tiles) {
+            if (P.queue && lane == 0) atomicAdd(P.tiles_finished, 1u);
+            continue;
+        }
     }
     const uint32_t imx = (tile % tiles_x) * 8 + (lane & 7);
     const uint32_t imy = (tile / tiles_x) * 4 + (lane >> 3);
@@ -857,10 +950,9 @@ raycast_kernel(const __grid_constant__ RayParams P) {
 
         if (R.intersects) {
             // a ray that is still marching after max_iters iterations hands the rest of its samples to the continuation
-            // queue (continue_kernel); with the queue full it finishes here (out-of-line copy of the march: an outer loop
+            // queue (continue_entry); with the queue full it finishes here (out-of-line copy of the march: an outer loop
             // around the inlined one made the compiler give up reconverging the warp inside the march, 4x the instructions)
-            const int resume = march_ray<FASTDIV, SKIP, SLAB>(P, s_t, R, 0, TSDF_B200_MAX_SAMPLES - 1,
-                                                              P.queue ? P.max_iters : 0x7fffffff, kh, s_hit, samples, dbg);
+            const int resume = march_ray<FASTDIV, SKIP, SLAB>(P, s_t, R, 0, TSDF_B200_MAX_SAMPLES - 1, max_iters, kh, s_hit, samples, dbg);
             if (resume >= 0) {
                 const uint32_t slot = atomicAdd(P.queue_count, 1u);
                 if (slot < P.queue_cap) { P.queue[slot] = make_int2((int)pix, resume); queued = true; }
@@ -883,7 +975,7 @@ raycast_kernel(const __grid_constant__ RayParams P) {
         }
 #endif
         if (queued) {
-            // continue_kernel writes this pixel
+            // the continuation writes this pixel
         } else if (SLAB) {
             // key: first hit along the ray wins the min over the ranks; the sample value rides in the low word
             const long long key = (kh >= 0) ? (((long long)kh << 32) | (long long)(uint32_t)__float_as_uint(s_hit)) : 0x7fffffffffffffffLL;
@@ -909,7 +1001,7 @@ raycast_kernel(const __grid_constant__ RayParams P) {
         if (lane == 0) { __threadfence(); completed = atomicAdd(P.tile_done + tile, 32u - nq) + (32u - nq) == 32u; }
         if (__shfl_sync(0xffffffffu, (int)completed, 0)) tile_completed(P, tile, s_tile[threadIdx.x >> 5], lane);
     } else if (!SLAB && P.mirror) {
-        // the tile as 4 rows of 24 floats; pixels handed to continue_kernel hold NaN here and are rewritten by it
+        // the tile as 4 rows of 24 floats; pixels handed to the continuation hold NaN here and are rewritten by it
         float *st = s_tile[threadIdx.x >> 5];
         st[3 * lane + 0] = ip[0]; st[3 * lane + 1] = ip[1]; st[3 * lane + 2] = ip[2];
         __syncwarp();
@@ -921,88 +1013,44 @@ raycast_kernel(const __grid_constant__ RayParams P) {
         }
         __syncwarp();
     }
+    if (P.queue) {
+        // every ray of this tile that is going to be set aside is in the queue now
+        __syncwarp();
+        if (lane == 0) { __threadfence(); atomicAdd(P.tiles_finished, 1u); }
+    }
     }
 
-    if (P.n_samples) {
-        for (int o = 16; o > 0; o >>= 1) samples += __shfl_down_sync(0xffffffffu, samples, o);
-        if (lane == 0 && samples) atomicAdd(P.n_samples, (unsigned long long)samples);
-    }
-}
-
-// Finishes the rays raycast_kernel set aside: one warp per queue entry (pixel, first remaining sample), lane l marching
-// the l-th of 32 equal pieces of the remaining sample range; the ray's first hit is the smallest hit sample over the lanes.
-template <bool FASTDIV, bool SKIP, bool SLAB>
-__global__ void __launch_bounds__(128, TSDF_RAY_MINB)
-continue_kernel(const __grid_constant__ RayParams P) {
-    __shared__ float s_t[TSDF_B200_RAY_TABLE_LEN];
-    __shared__ __align__(16) float s_tile[4][96];
-    for (int i = threadIdx.x; i < TSDF_B200_RAY_TABLE_LEN; i += blockDim.x) s_t[i] = P.table[i];
-    __syncthreads();
-    const int lane = threadIdx.x & 31;
-    const uint32_t warps_total = gridDim.x * (blockDim.x >> 5);
-    const uint32_t n = min(*P.queue_count, P.queue_cap);
-    uint32_t samples = 0;
-    for (uint32_t e = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); e < n; e += warps_total) {
-        const int2 entry = P.queue[e];
-        const size_t pix = (size_t)entry.x;
-        const uint32_t imx = (uint32_t)entry.x % P.width, imy = (uint32_t)entry.x / P.width;
-        const RaySetup R = ray_setup(P, imx, imy);
-        // samples the ray still has: k_end is only an estimate of the last one, the final piece runs to the end of the table
-        const int k0 = entry.y;
-        const int k_end = min(max((int)fminf(R.max_t * __frcp_rn(P.step), 5000.0f) + 1, k0), TSDF_B200_MAX_SAMPLES - 1);
-        const int len = k_end - k0 + 1;
-        // The remaining samples are cut into kRounds * 32 chunks; in round r lane l marches chunk 32 r + l.  Neighbouring
-        // chunks run side by side, so a stretch of expensive samples (a ray skimming a surface) spreads over many lanes
-        // instead of landing in one lane's piece; a round whose chunks all start behind the best hit so far is skipped.
-        constexpr int kRounds = TSDF_RAY_ROUNDS, kChunks = 32 * kRounds;
-        int kh = -1;
-        float s_hit = 0.0f;
-        RayDebug dbg = { 0, 0, 0, 0, 0 };
-        long long key = 0x7fffffffffffffffLL;
-        for (int r = 0; r < kRounds; r++) {
-            const int c = 32 * r + lane;
-            const int first = k0 + (int)((long long)len * c / kChunks);
-            const int last = c == kChunks - 1 ? TSDF_B200_MAX_SAMPLES - 1 : k0 + (int)((long long)len * (c + 1) / kChunks) - 1;
-            if (first <= last && kh < 0) march_ray<FASTDIV, SKIP, SLAB>(P, s_t, R, first, last, 0x7fffffff, kh, s_hit, samples, dbg);
-            key = (kh >= 0) ? (((long long)kh << 32) | (long long)(uint32_t)__float_as_uint(s_hit)) : 0x7fffffffffffffffLL;
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) key = min(key, __shfl_xor_sync(0xffffffffu, key, o));
-            if (key != 0x7fffffffffffffffLL) break;           // later rounds only hold later samples
-        }
-        if (lane == 0) {
-            if (SLAB) {
-                if (P.keys_min) { if (key != 0x7fffffffffffffffLL) atomicMin(P.keys_min + pix, key); }
-                else P.keys[pix] = key;
-            } else {
-                float ip[3] = { CUDART_NAN_F, CUDART_NAN_F, CUDART_NAN_F };
-                int k_hit = -1;
-                if (key != 0x7fffffffffffffffLL) {
-                    k_hit = (int)(key >> 32);
-                    hit_vertex(P, R, s_t[k_hit], __uint_as_float((uint32_t)(key & 0xffffffffLL)), ip);
-                }
-                if (P.n_out) {
-                    for (uint32_t d = 0; d < P.n_out; d++) {
-                        float *v = P.out[d] + 3 * pix;
-                        v[0] = ip[0]; v[1] = ip[1]; v[2] = ip[2];
+    // ---- no tile left: this warp turns to the rays that were set aside (round 2; a second kernel used to do this after the
+    // march had drained, 50 us during which the chip was all but idle).  It claims the next queue slot and waits for a ray to
+    // appear in it, or for the last tile to finish — from then on a slot that is still empty stays empty.  Whether a block of
+    // this grid is resident or not does not matter: only warps that hold a tile are waited for.
+    if (P.queue) {
+        float *st = s_tile[threadIdx.x >> 5];
+        while (true) {
+            long long raw = -1;
+            if (lane == 0) {
+                const uint32_t c = atomicAdd(P.queue_head, 1u);
+                if (c < P.queue_cap) {
+                    const volatile long long *slot = reinterpret_cast<const volatile long long *>(P.queue + c);
+                    for (uint32_t polls = 0; polls < (1u << 22); polls++) {       // (bounded: ~1 s)
+                        raw = *slot;
+                        if ((int)(raw >> 32) >= 0) break;                           // int2 (pixel, sample): the sample is never negative
+                        if (*reinterpret_cast<const volatile unsigned int *>(P.tiles_finished) >= n_work) {
+                            __threadfence();
+                            raw = *slot;
+                            break;
+                        }
+                        __nanosleep(200);
                     }
-                } else {
-                    P.vertices[3 * pix + 0] = ip[0];
-                    P.vertices[3 * pix + 1] = ip[1];
-                    P.vertices[3 * pix + 2] = ip[2];
-                    if (P.khit && !P.debug_iters) P.khit[pix] = k_hit;
-                    if (P.mirror && !P.tile_done) { P.mirror[3 * pix + 0] = ip[0]; P.mirror[3 * pix + 1] = ip[1]; P.mirror[3 * pix + 2] = ip[2]; }
                 }
             }
-        }
-        __syncwarp();
-        if (!SLAB && P.tile_done) {
-            // pool kernel bookkeeping: this ray may have been the last one its tile waited for
-            const uint32_t tile = (imy / 4) * (P.width / 8) + imx / 8;
-            bool completed = false;
-            if (lane == 0) { __threadfence(); completed = atomicAdd(P.tile_done + tile, 1u) == 31u; }
-            if (__shfl_sync(0xffffffffu, (int)completed, 0)) tile_completed(P, tile, s_tile[threadIdx.x >> 5], lane);
+            raw = __shfl_sync(0xffffffffu, raw, 0);
+            const int2 entry = make_int2((int)(uint32_t)(raw & 0xffffffffLL), (int)(raw >> 32));
+            if (entry.y < 0) break;
+            continue_entry<FASTDIV, SKIP, SLAB>(P, s_t, entry, lane, st, samples);
         }
     }
+
     if (P.n_samples) {
         for (int o = 16; o > 0; o >>= 1) samples += __shfl_down_sync(0xffffffffu, samples, o);
         if (lane == 0 && samples) atomicAdd(P.n_samples, (unsigned long long)samples);
@@ -1161,7 +1209,7 @@ static int fill_params(RayParams &P, const float *d_dist, uint32_t nx, uint32_t 
     P.debug_iters = getenv("TSDF_B200_DEBUG_ITERS") ? atoi(getenv("TSDF_B200_DEBUG_ITERS")) : 0;
     P.tile_first = 0; P.tile_stride = 1; P.n_out = 0; P.mirror = nullptr;
     P.normals = nullptr; P.mirror_n = nullptr; P.tile_done = nullptr; P.tile_deps = nullptr;
-    P.queue = nullptr; P.queue_count = nullptr; P.queue_cap = 0;
+    P.queue = nullptr; P.queue_count = nullptr; P.queue_head = nullptr; P.tiles_finished = nullptr; P.cap_word = nullptr; P.queue_cap = 0;
     // (round 2, after the march_step rewrite: 48 / 64 / 80 / 96 / 128 / 160 iterations -> 283 / 259 / 257 / 273 / 302 / 327 us on
     // the bench frames, 470 / 431 / 404 / 398 / 417 / 433 us on frame 500 — profiles/r02u_ray_caps_march_step.txt)
     static const int cap = getenv("TSDF_B200_RAY_CAP") ? atoi(getenv("TSDF_B200_RAY_CAP")) : 80;
@@ -1195,10 +1243,26 @@ static int launch_march(RayParams &P, int fastdiv, cudaStream_t s, unsigned int 
         const size_t nb = (size_t)P.nbx * P.nby * P.nbz;
         uint8_t *cd = const_cast<uint8_t *>(P.occ) + nb, *tmp = cd + nb;
         if (P.nby > 65535 || P.nbz > 65535) return TSDF_B200_EINVAL;
-        // scratch third of the buffer: [work counter | queue length | continuation queue]
+        // scratch third of the buffer: [work counter | queue slots handed out | queue slots claimed | tiles finished | queue]
         uint8_t *word = (uint8_t *)(((uintptr_t)tmp + 7) & ~(uintptr_t)7);
-        const bool have_words = word + 8 <= tmp + nb;
-        const size_t n_words = 2;
+        const size_t n_words = kMarchWords;
+        const bool have_words = word + n_words * 4 <= tmp + nb;
+        size_t queue_cap = 0;
+        if (have_words && P.max_iters != 0x7fffffff) {
+            queue_cap = (size_t)(tmp + nb - (word + n_words * 4)) / sizeof(int2);
+            if (queue_cap > 65536) queue_cap = 65536;
+            if (queue_cap < 64) queue_cap = 0;
+        }
+        const int n_queue_words = (int)(2 * queue_cap);
+        // iteration cap: fixed (TSDF_B200_RAY_CAP), or 64 / 80 by the number of rays the previous frame set aside (march_reset;
+        // thresholds from the orbit, profiles/r02v_adaptive_cap.txt: with 64, more than 6.3 % of the rays; with 80, fewer than 3.7 %)
+        MarchReset reset;
+        reset.words = have_words ? reinterpret_cast<unsigned int *>(word) : nullptr;
+        reset.n_queue_words = n_queue_words;
+        const bool adaptive = !getenv("TSDF_B200_RAY_CAP") && queue_cap;
+        reset.cap_lo = adaptive ? 64 : P.max_iters; reset.cap_hi = adaptive ? 80 : P.max_iters;
+        const double rays = (double)P.width * P.height / (P.tile_stride > 1 ? P.tile_stride : 1);
+        reset.thr_lo = (unsigned int)(0.037 * rays); reset.thr_hi = (unsigned int)(0.063 * rays);
         // completion counters (the caller's, zero between launches) for fused normals
         if (have_words && !SLAB && aligned && tile_words && P.tile_stride <= 1 && want_normals) {
             P.tile_done = tile_words;
@@ -1210,7 +1274,7 @@ static int launch_march(RayParams &P, int fastdiv, cudaStream_t s, unsigned int 
         static const bool byte_passes = getenv("TSDF_B200_DIST_BYTES") != nullptr;
         // bit rows: up to 128 bricks along x and y
         const int wpr = (int)((P.nbx + 63) / 64), rpl = (int)((P.nby + 31) / 32);
-        void (*bits_kernel)(const uint8_t *, uint8_t *, int, int, int, unsigned int *, int) = nullptr;
+        void (*bits_kernel)(const uint8_t *, uint8_t *, int, int, int, MarchReset) = nullptr;
         int R = 0;
         if (!global_passes && !byte_passes && wpr <= 2 && rpl <= 4) {
             R = rpl <= 1 ? 1 : (rpl <= 2 ? 2 : 4);
@@ -1226,34 +1290,37 @@ static int launch_march(RayParams &P, int fastdiv, cudaStream_t s, unsigned int 
             if (smem_bits > 48 * 1024)
                 TSDF_CUDA_TRY(cudaFuncSetAttribute(bits_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bits));
             bits_kernel<<<(P.nbz + kDistOut - 1) / kDistOut, 1024, smem_bits, s>>>(
-                P.occ, cd, (int)P.nbx, (int)P.nby, (int)P.nbz, have_words ? reinterpret_cast<unsigned int *>(word) : nullptr, (int)n_words);
+                P.occ, cd, (int)P.nbx, (int)P.nby, (int)P.nbz, reset);
         } else if (smem_xy <= 48 * 1024 && smem_z <= 48 * 1024 && !global_passes) {
-            distance_xy_kernel<<<P.nbz, 1024, smem_xy, s>>>(P.occ, cd, (int)P.nbx, (int)P.nby,
-                                                           have_words ? reinterpret_cast<unsigned int *>(word) : nullptr, (int)n_words);
+            distance_xy_kernel<<<P.nbz, 1024, smem_xy, s>>>(P.occ, cd, (int)P.nbx, (int)P.nby, reset);
             distance_z_kernel<<<P.nby, 1024, smem_z, s>>>(cd, (int)P.nbx, (int)P.nby, (int)P.nbz);
         } else {
             const dim3 g((P.nbx + 255) / 256, P.nby, P.nbz);
             distance_pass_kernel<0, true><<<g, 256, 0, s>>>(P.occ, cd, (int)P.nbx, (int)P.nby, (int)P.nbz);
             distance_pass_kernel<1, false><<<g, 256, 0, s>>>(cd, tmp, (int)P.nbx, (int)P.nby, (int)P.nbz);
             distance_pass_kernel<2, false><<<g, 256, 0, s>>>(tmp, cd, (int)P.nbx, (int)P.nby, (int)P.nbz);
-            if (have_words) TSDF_CUDA_TRY(cudaMemsetAsync(word, 0, n_words * 4, s));
+            if (have_words) {      // (no kernel to carry the cap's state here: the fixed cap)
+                TSDF_CUDA_TRY(cudaMemsetAsync(word, 0, n_words * 4, s));
+                if (n_queue_words) TSDF_CUDA_TRY(cudaMemsetAsync(word + n_words * 4, 0xff, (size_t)n_queue_words * 4, s));
+            }
         }
         P.occ_d = cd;
         if (have_words) {
             P.tile_counter = reinterpret_cast<unsigned int *>(word);
-            uint8_t *q = (uint8_t *)(((uintptr_t)(word + n_words * 4) + 7) & ~(uintptr_t)7);
-            const size_t room = q < tmp + nb ? (size_t)(tmp + nb - q) / sizeof(int2) : 0;
-            if (room >= 64 && P.max_iters != 0x7fffffff) {
+            if (queue_cap) {
                 P.queue_count = P.tile_counter + 1;
-                P.queue = reinterpret_cast<int2 *>(q);
-                P.queue_cap = (uint32_t)(room < 0x7fffffffu ? room : 0x7fffffffu);
+                P.queue_head = P.tile_counter + 2;
+                P.tiles_finished = P.tile_counter + 3;
+                P.cap_word = P.tile_counter + 4;
+                P.queue = reinterpret_cast<int2 *>(word + n_words * 4);
+                P.queue_cap = (uint32_t)queue_cap;
             }
         }
     }
     dim3 block(128);
     uint32_t n_tiles = n_tiles_all;
     if (P.tile_stride > 1) n_tiles = (n_tiles + P.tile_stride - 1) / P.tile_stride;      // tiles this rank marches
-    auto launch = [&](auto kernel, auto tail_kernel) -> int {
+    auto launch = [&](auto kernel) -> int {
         // resident blocks on this device (queried once per kernel variant)
         static int resident = 0;
         if (resident == 0) {
@@ -1265,17 +1332,11 @@ static int launch_march(RayParams &P, int fastdiv, cudaStream_t s, unsigned int 
         }
         const uint32_t blocks = (n_tiles + 3) / 4 < (uint32_t)resident ? (n_tiles + 3) / 4 : (uint32_t)resident;
         kernel<<<blocks, block, 0, s>>>(P);
-        if (P.queue) tail_kernel<<<resident, block, 0, s>>>(P);
         return (int)cudaGetLastError();
     };
     int rc;
-    if (fastdiv) {
-        rc = P.occ ? launch(raycast_kernel<true, true, SLAB>, continue_kernel<true, true, SLAB>)
-                   : launch(raycast_kernel<true, false, SLAB>, continue_kernel<true, false, SLAB>);
-    } else {
-        rc = P.occ ? launch(raycast_kernel<false, true, SLAB>, continue_kernel<false, true, SLAB>)
-                   : launch(raycast_kernel<false, false, SLAB>, continue_kernel<false, false, SLAB>);
-    }
+    if (fastdiv) rc = P.occ ? launch(raycast_kernel<true, true, SLAB>) : launch(raycast_kernel<true, false, SLAB>);
+    else         rc = P.occ ? launch(raycast_kernel<false, true, SLAB>) : launch(raycast_kernel<false, false, SLAB>);
     if (rc) return rc;
     if (want_normals && !P.normals) {
         // not fused (no room for the counters, image not tile-aligned, pool kernel switched off): the normals kernel, and a copy

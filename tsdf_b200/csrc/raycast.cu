@@ -816,6 +816,7 @@ __device__ __forceinline__ void tile_completed(const RayParams &P, uint32_t tile
 #ifndef TSDF_RAY_ROUNDS
 #define TSDF_RAY_ROUNDS 4
 #endif
+
 #ifndef TSDF_RAY_MINB
 #define TSDF_RAY_MINB 6
 #endif

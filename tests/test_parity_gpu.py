@@ -880,3 +880,32 @@ def test_brick_distance_grid_equals_chessboard_transform(G):
         assert np.array_equal(got, want), f"grid {nb}, density {density}: {int((got != want).sum())} bricks differ"
         assert np.array_equal(occ[:nbr].cpu().numpy(), flags), "flags modified"
         del dist
+
+
+def test_depth_pyramid_equals_max_pooling(G):
+    """tsdf_b200_depth_stage: level l of the culling pyramid holds the largest depth of every 2^l x 2^l pixel tile (levels 3 up
+    to the single-entry top), for image sizes with and without whole tiles and rows that are not 16-byte multiples."""
+    import ctypes as C
+    import torch
+    from tsdf_b200.capi import lib, check
+    rng = np.random.default_rng(11)
+    for w, h in ((640, 480), (322, 241), (64, 48), (8, 8), (1000, 37)):
+        depth = rng.integers(0, 65536, size=(h, w), dtype=np.uint16)
+        depth[rng.random((h, w)) < 0.3] = 0
+        d = torch.from_numpy(depth).cuda()
+        st = torch.zeros((lib.tsdf_b200_depth_staged_bytes(w, h) + 1) // 2, dtype=torch.int16, device="cuda")
+        check(lib.tsdf_b200_depth_stage(C.c_void_p(d.data_ptr()), w, h, C.c_void_p(st.data_ptr()), None), "depth_stage")
+        torch.cuda.synchronize()
+        got = st.cpu().numpy().view(np.uint16)
+        off, level = 0, 3
+        while True:
+            t = 1 << level
+            wl, hl = (w + t - 1) // t, (h + t - 1) // t
+            pad = np.zeros((hl * t, wl * t), np.uint16)
+            pad[:h, :w] = depth
+            want = pad.reshape(hl, t, wl, t).max(axis=(1, 3))
+            assert np.array_equal(got[off:off + wl * hl].reshape(hl, wl), want), f"{w}x{h}: pyramid level {level} differs"
+            off += wl * hl
+            if wl == 1 and hl == 1:
+                break
+            level += 1

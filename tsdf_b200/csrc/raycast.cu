@@ -938,6 +938,8 @@ raycast_kernel(const __grid_constant__ RayParams P) {
     const uint32_t imy = (tile / tiles_x) * 4 + (lane >> 3);
     float ip[3] = { CUDART_NAN_F, CUDART_NAN_F, CUDART_NAN_F };
     bool queued = false;
+    uint32_t queue_slot = 0;
+    int queue_resume = 0;
     if (imx < P.width && imy < P.height) {
         const size_t pix = (size_t)imy * P.width + imx;
         const RaySetup R = ray_setup(P, imx, imy);
@@ -955,8 +957,9 @@ raycast_kernel(const __grid_constant__ RayParams P) {
             // around the inlined one made the compiler give up reconverging the warp inside the march, 4x the instructions)
             const int resume = march_ray<FASTDIV, SKIP, SLAB>(P, s_t, R, 0, TSDF_B200_MAX_SAMPLES - 1, max_iters, kh, s_hit, samples, dbg);
             if (resume >= 0) {
+                // (the slot is taken now, the entry is written after this tile's own stores — see below)
                 const uint32_t slot = atomicAdd(P.queue_count, 1u);
-                if (slot < P.queue_cap) { P.queue[slot] = make_int2((int)pix, resume); queued = true; }
+                if (slot < P.queue_cap) { queued = true; queue_slot = slot; queue_resume = resume; }
                 else march_ray_cold<FASTDIV, SKIP, SLAB>(P, s_t, R, resume, kh, s_hit, samples, dbg);
             }
             if (kh >= 0 && !SLAB) hit_vertex(P, R, s_t[kh], s_hit, ip);
@@ -1015,7 +1018,11 @@ raycast_kernel(const __grid_constant__ RayParams P) {
         __syncwarp();
     }
     if (P.queue) {
-        // every ray of this tile that is going to be set aside is in the queue now
+        // The rays of this tile that are set aside enter the queue only now: whoever finishes one of them may start at once,
+        // and its single-pixel store into the mirror has to come after this warp's store of the whole tile (which holds NaN
+        // for that pixel).
+        if (!SLAB && P.mirror && !P.tile_done) __threadfence_system();
+        if (queued) P.queue[queue_slot] = make_int2((int)(imy * P.width + imx), queue_resume);
         __syncwarp();
         if (lane == 0) { __threadfence(); atomicAdd(P.tiles_finished, 1u); }
     }

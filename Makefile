@@ -8,7 +8,7 @@ NVCCFLAGS := $(ARCH) -O3 -std=c++17 -lineinfo -fmad=false -Xcompiler -fPIC,-Wall
 CSRC      := tsdf_b200/csrc
 OBJS      := $(CSRC)/integrate.o $(CSRC)/raycast.o $(CSRC)/misc.o $(CSRC)/volume.o $(CSRC)/mc.o $(CSRC)/bilateral.o $(CSRC)/exchange.o $(CSRC)/multi.o
 
-all: lib oracle classes
+all: lib oracle classes class_e2e
 
 lib: tsdf_b200/libtsdf_b200.so
 
@@ -35,11 +35,12 @@ HOST      := tsdf_b200/host
 HOSTSRC   := $(wildcard $(HOST)/*.cpp)
 HOSTOBJ   := $(HOSTSRC:.cpp=.o)
 EIGEN_INC ?= tsdf_b200/compat
-CXXFLAGS  := -O2 -std=c++14 -fPIC -Wall -Wno-unused-function -I$(EIGEN_INC) -I/usr/local/cuda/include
+# TSDF_B200_PINNED_EIGEN: Dynamic matrices of the Eigen stand-in take their storage from tsdf_b200_host_alloc (pinned pool)
+CXXFLAGS  := -O2 -std=c++14 -fPIC -Wall -Wno-unused-function -DTSDF_B200_PINNED_EIGEN -I$(EIGEN_INC) -I/usr/local/cuda/include
 
 classes: tsdf_b200/libtsdf_b200_classes.so
 
-$(HOST)/%.o: $(HOST)/%.cpp $(wildcard tsdf_b200/include/*.hpp) include/tsdf_b200.h
+$(HOST)/%.o: $(HOST)/%.cpp $(wildcard tsdf_b200/include/*.hpp) $(wildcard tsdf_b200/compat/*.hpp) include/tsdf_b200.h
 	g++ $(CXXFLAGS) -c $< -o $@
 
 tsdf_b200/libtsdf_b200_classes.so: $(HOSTOBJ) tsdf_b200/libtsdf_b200.so
@@ -55,6 +56,11 @@ kinfu: classes
 	g++ $(CXXFLAGS) -include cstring -include cstdlib -include cstdint -o build/kinfu build/dropin/Tools/kinfu.cpp \
 	    -Ltsdf_b200 -ltsdf_b200_classes -ltsdf_b200 -Wl,-rpath,$(abspath tsdf_b200)
 
+# End-to-end timing of the class layer the way kinfu.cpp drives it (tools/class_e2e.cpp; bench.py runs it when it exists)
+class_e2e: classes
+	mkdir -p build
+	g++ $(CXXFLAGS) -o build/class_e2e tools/class_e2e.cpp -Ltsdf_b200 -ltsdf_b200_classes -ltsdf_b200 -Wl,-rpath,$(abspath tsdf_b200)
+
 oracle: oracle/liboracle.so
 
 oracle/liboracle.so: oracle/tsdf_oracle.c tsdf_b200/csrc/mc_tables.h
@@ -66,4 +72,4 @@ ref:
 clean:
 	rm -f $(CSRC)/*.o $(HOST)/*.o tsdf_b200/libtsdf_b200.so tsdf_b200/libtsdf_b200_classes.so oracle/liboracle.so
 
-.PHONY: all lib oracle ref clean classes kinfu variant dbg
+.PHONY: all lib oracle ref clean classes kinfu variant dbg class_e2e

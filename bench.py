@@ -254,6 +254,35 @@ def time_ref_cuda(size, first_frame, n_frames):
     return out
 
 
+
+def class_layer_e2e(size, frames, cams, warmup, steps, W, H):
+    """The same frames through the drop-in C++ classes (TSDFVolume::integrate / ::raycast, Eigen result matrices declared per
+    frame, as the reference's kinfu.cpp does): tools/class_e2e.cpp, built by `make class_e2e`.  None when the binary is absent."""
+    import struct, subprocess, tempfile
+    exe = os.path.join(ROOT, "build", "class_e2e")
+    if not os.path.exists(exe):
+        return None
+    n = warmup + steps
+    try:
+        with tempfile.NamedTemporaryFile(suffix=".bin", delete=False) as f:
+            f.write(struct.pack("<4If", size, W, H, n, PHYS[0]))
+            f.write(np.asarray(cams[0].k, np.float32).tobytes())
+            for i in range(n):
+                f.write(np.asarray(cams[i].pose, np.float32).tobytes())
+                f.write(np.ascontiguousarray(frames[i], np.uint16).tobytes())
+            path = f.name
+        out = subprocess.run([exe, path, str(warmup)], capture_output=True, text=True, timeout=600)
+        os.unlink(path)
+        lines = [l for l in out.stdout.splitlines() if l.startswith("{")]
+        if not lines:
+            return {"error": f"rc {out.returncode}: " + (out.stdout + out.stderr)[-300:]}
+        r = json.loads(lines[-1])
+        return {"value": r["frames_per_s"], "unit": "frames/s", "ms_per_step": r["ms_per_frame"], "frames": r["frames"],
+                "api": "TSDFVolume::integrate + TSDFVolume::raycast of the drop-in C++ class layer, DepthImage pixels and the Eigen "
+                       "result matrices (declared per frame, like kinfu.cpp:174-181) in the library's pinned pool (tools/class_e2e.cpp)"}
+    except Exception as e:      # the tool is an extra: never fail the bench line for it
+        return {"error": repr(e)[:200]}
+
 def main():
     args = parse()
     rank = int(os.environ.get("RANK", "0"))
@@ -404,7 +433,7 @@ def main():
                     "hit_rate_source": prof.get("raycast_source")})
 
     # ---- e2e: level-2 C-ABI with host buffers ---------------------------------------------------------------------------
-    e2e, e2e_pageable = R["e2e_sharded"], None
+    e2e, e2e_pageable, e2e_classes = R["e2e_sharded"], None, None
     if not args.no_e2e and world == 1:
         vol = Volume(n, PHYS)
         mats = [(colmajor(c.inv_pose), colmajor(c.k), colmajor(c.kinv), colmajor(c.pose)) for c in cams]
@@ -443,6 +472,7 @@ def main():
                         "api": "the same calls with pageable (malloc'ed) depth and result buffers — what kinfu's DepthImage::data() "
                                "and Eigen matrices are (the driver stages the copies)"}
         vol.close()
+        e2e_classes = class_layer_e2e(size, frames, cams, Wm, K, W, H)
 
     # ---- baselines on the same box: CPU restatement (whole frames), reference CUDA --------------------------------------
     cpu_baseline, ref_cuda = None, None
@@ -488,7 +518,7 @@ def main():
             "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": K, "warmup": Wm,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic", "config": cfg,
-            "clocks": R["clocks"], "e2e": e2e, "e2e_pageable": e2e_pageable, "gpu_launches": R["launches_per_step"] * K,
+            "clocks": R["clocks"], "e2e": e2e, "e2e_pageable": e2e_pageable, "e2e_classes": e2e_classes, "gpu_launches": R["launches_per_step"] * K,
             "roofline": roofline, "cpu_baseline": cpu_baseline, "ref_cuda": ref_cuda, "raycast": raycast, "extra": extra,
         }
         print(json.dumps(out))

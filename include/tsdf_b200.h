@@ -343,6 +343,13 @@ int tsdf_b200_volume_set_deformation(tsdf_b200_volume *v, const float *host_node
 /* Device -> host copies for tests and tools. */
 int tsdf_b200_volume_read(const tsdf_b200_volume *v, float *host_dist, float *host_weight);
 
+/* Host memory for buffers that cross the bus every frame (depth maps, vertex / normal maps).  Blocks of 256 KiB and more come
+ * from a pool of pinned (page-locked, device-addressable) memory and go back to it when freed — a caller that allocates its
+ * result buffers per frame, as kinfu.cpp does with its Eigen matrices, pays for the pinning once; smaller blocks, and any block
+ * when there is no CUDA device, come from malloc.  tsdf_b200_volume_raycast recognises pinned buffers by itself.            */
+void *tsdf_b200_host_alloc(size_t bytes);
+void tsdf_b200_host_free(void *p);
+
 /* TSDFVolume::integrate (TSDF/TSDFVolume.cu:861-902): host depth map, camera matrices as
  * Camera::inverse_pose()/k()/kinv() .data().  Returns when the depth map has been read; the fusion
  * completes in stream order before any later call on the volume returns data (as if synchronous;

@@ -91,3 +91,26 @@ def test_exchange_entry_points_validate_arguments(built):
     assert lib.tsdf_b200_peer_open(None, C.byref(p)) == -1
     assert lib.tsdf_b200_peer_alloc(0, C.byref(p), None) == -1
     assert lib.tsdf_b200_peer_close(None) == 0 and lib.tsdf_b200_peer_free(None) == 0
+
+
+def test_host_pool_without_a_device(built):
+    """tsdf_b200_host_alloc / _free: small blocks and — on a box without a CUDA device — large ones come from malloc; blocks are
+    writable, free accepts NULL; tsdf_b200_raycast_fused validates its arguments like tsdf_b200_raycast_mirrored."""
+    import ctypes as C
+    from tsdf_b200 import capi
+    lib = capi.lib
+    for size in (1, 1000, 300 * 1024, 4 << 20):
+        p = lib.tsdf_b200_host_alloc(size)
+        assert p
+        C.memset(p, 0x5a, size)
+        assert C.string_at(p + size - 1, 1) == b"\x5a"
+        lib.tsdf_b200_host_free(C.c_void_p(p))
+    lib.tsdf_b200_host_free(None)
+    assert lib.tsdf_b200_raycast_tile_counters(640, 480) == 2 * 80 * 120
+    assert lib.tsdf_b200_raycast_tile_counters(9, 5) == 2 * 2 * 2
+    f3 = capi.fptr(np.ones(3, np.float32)); f9 = capi.fptr(np.eye(3, dtype=np.float32).reshape(-1))
+    d = C.c_void_p(16)
+    # no normal map / ragged image with mirrors / misaligned mirror
+    assert lib.tsdf_b200_raycast_fused(d, 8, 8, 8, f3, f3, f3, 1.0, f3, f9, f9, 8, 4, d, None, d, None, None, None, None, None, 0, None) == -1
+    assert lib.tsdf_b200_raycast_fused(d, 8, 8, 8, f3, f3, f3, 1.0, f3, f9, f9, 10, 4, d, None, d, d, d, d, None, None, 0, None) == -1
+    assert lib.tsdf_b200_raycast_fused(d, 8, 8, 8, f3, f3, f3, 1.0, f3, f9, f9, 8, 4, d, None, d, d, C.c_void_p(24), d, None, None, 0, None) == -1

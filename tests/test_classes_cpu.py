@@ -15,7 +15,7 @@ def build_class_tests():
     subprocess.check_call(["make", "-C", ROOT, "-j8", "classes"], stdout=subprocess.DEVNULL)
     os.makedirs(BUILD, exist_ok=True)
     exe = os.path.join(BUILD, "class_tests")
-    subprocess.check_call(["g++", "-O1", "-std=c++14", "-Wall", "-I" + os.path.join(ROOT, "tsdf_b200", "compat"),
+    subprocess.check_call(["g++", "-O1", "-std=c++14", "-Wall", "-DTSDF_B200_PINNED_EIGEN", "-I" + os.path.join(ROOT, "tsdf_b200", "compat"),
                            "-I/usr/local/cuda/include", "-o", exe, os.path.join(ROOT, "tests", "cpp", "class_tests.cpp"),
                            "-L" + os.path.join(ROOT, "tsdf_b200"), "-ltsdf_b200_classes", "-ltsdf_b200",
                            "-Wl,-rpath," + os.path.join(ROOT, "tsdf_b200")])

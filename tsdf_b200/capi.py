@@ -34,6 +34,8 @@ SIGNATURES = {
     "tsdf_b200_debug_integrate_variant": (None, [C.c_int]),
     "tsdf_b200_occupancy_bytes": (C.c_size_t, [_u32, _u32, _u32]),
     "tsdf_b200_occupancy_rebuild": (C.c_int, [_vp, _u32, _u32, _u32, C.c_float, _vp, _vp]),
+    "tsdf_b200_host_alloc": (C.c_void_p, [C.c_size_t]),
+    "tsdf_b200_host_free": (None, [_vp]),
     "tsdf_b200_ray_table": (C.c_int, [C.c_float, _vp, _vp]),
     "tsdf_b200_raycast": (C.c_int, [_vp, _u32, _u32, _u32, _f, _f, _f, C.c_float, _f, _f, _f, _u32, _u32,
                                     _vp, _vp, _vp, _vp, _vp, _vp]),

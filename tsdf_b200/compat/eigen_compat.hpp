@@ -19,6 +19,9 @@
 #include <limits>
 #include <ostream>
 #include <type_traits>
+#include <cstdlib>
+#include <new>
+#include <utility>
 #include <vector>
 
 namespace Eigen {
@@ -29,6 +32,31 @@ typedef std::ptrdiff_t Index;
 template <typename T, int R, int C> class Matrix;
 
 namespace compat {
+// Where the storage of Dynamic matrices comes from.  The drop-in class layer is built with TSDF_B200_PINNED_EIGEN: large blocks
+// then come from the library's pool of pinned host memory (tsdf_b200_host_alloc), so that the result matrices a caller
+// declares per frame — kinfu.cpp does — are buffers the device can write while the raycast runs (tsdf_b200_volume_raycast
+// mirrors both maps into pinned buffers; a pageable buffer gets a staged copy afterwards, at half the frame rate).  Like
+// Eigen's own, the storage is NOT zero-filled by resize().
+#ifdef TSDF_B200_PINNED_EIGEN
+extern "C" void *tsdf_b200_host_alloc(size_t bytes);
+extern "C" void tsdf_b200_host_free(void *p);
+inline void *raw_alloc(size_t bytes) { return tsdf_b200_host_alloc(bytes); }
+inline void raw_free(void *p) { tsdf_b200_host_free(p); }
+#else
+inline void *raw_alloc(size_t bytes) { return std::malloc(bytes ? bytes : 1); }
+inline void raw_free(void *p) { std::free(p); }
+#endif
+template <typename T> struct HostAllocator {
+    typedef T value_type;
+    HostAllocator() {}
+    template <typename U> HostAllocator(const HostAllocator<U> &) {}
+    T *allocate(size_t n) { void *p = raw_alloc(n * sizeof(T)); if (!p) throw std::bad_alloc(); return static_cast<T *>(p); }
+    void deallocate(T *p, size_t) { raw_free(p); }
+    template <typename U> void construct(U *p) { ::new (static_cast<void *>(p)) U; }          // default-initialised: no fill
+    template <typename U, typename... A> void construct(U *p, A &&...a) { ::new (static_cast<void *>(p)) U(std::forward<A>(a)...); }
+    template <typename U> bool operator==(const HostAllocator<U> &) const { return true; }
+    template <typename U> bool operator!=(const HostAllocator<U> &) const { return false; }
+};
 // Storage: in-object array for fixed sizes, std::vector when the column count is Dynamic.
 template <typename T, int R, int C> struct Storage {
     T v[R * C];
@@ -40,7 +68,7 @@ template <typename T, int R, int C> struct Storage {
     void resize(Index r, Index c) { assert(r == R && c == C); (void)r; (void)c; }
 };
 template <typename T, int R> struct Storage<T, R, Dynamic> {
-    std::vector<T> v;
+    std::vector<T, HostAllocator<T> > v;
     Index n_cols;
     Storage() : n_cols(0) {}
     T *ptr() { return v.data(); }

@@ -11,6 +11,9 @@
 #include <stdlib.h>
 #include <string.h>
 #include <new>
+#include <map>
+#include <mutex>
+#include <unordered_map>
 
 // (tsdf_b200_raycast_ex is declared in include/tsdf_b200.h)
 
@@ -457,4 +460,56 @@ extern "C" int tsdf_b200_volume_extract_mesh(const tsdf_b200_volume *cv, float *
     *n_vertices_out = 0;
     if (v->multi) return tsdf::multi_extract_mesh(v, d_vertices_out, n_vertices_out);
     return tsdf_b200_mc_extract(v->d_dist, v->nx, v->ny, v->nz, 0, 0, v->nz - 1, v->vs, v->off, d_vertices_out, n_vertices_out, v->stream);
+}
+
+// ---- pooled pinned host memory (tsdf_b200_host_alloc / _free) ----------------------------------------------------------------
+namespace {
+struct HostPool {
+    std::mutex m;
+    std::unordered_map<void *, size_t> pinned;          // every live pinned block, in use or pooled
+    std::multimap<size_t, void *> free_blocks;          // pooled blocks by size
+    size_t pooled_bytes = 0;
+};
+HostPool &host_pool() { static HostPool *p = new HostPool(); return *p; }     // never destroyed: outlives static destructors
+constexpr size_t kPinnedMin = 256 * 1024, kPoolMax = (size_t)1 << 30;
+}  // namespace
+
+extern "C" void *tsdf_b200_host_alloc(size_t bytes) {
+    if (bytes < kPinnedMin) return malloc(bytes ? bytes : 1);
+    HostPool &P = host_pool();
+    {
+        std::lock_guard<std::mutex> lk(P.m);
+        auto it = P.free_blocks.lower_bound(bytes);
+        if (it != P.free_blocks.end() && it->first <= bytes + bytes / 4) {      // a pooled block of (nearly) this size
+            void *p = it->second;
+            P.pooled_bytes -= it->first;
+            P.free_blocks.erase(it);
+            return p;
+        }
+    }
+    void *p = nullptr;
+    if (cudaHostAlloc(&p, bytes, cudaHostAllocPortable) != cudaSuccess) {
+        cudaGetLastError();                          // no device, or no pinnable memory left: ordinary memory does the job
+        return malloc(bytes);
+    }
+    std::lock_guard<std::mutex> lk(P.m);
+    P.pinned[p] = bytes;
+    return p;
+}
+
+extern "C" void tsdf_b200_host_free(void *p) {
+    if (!p) return;
+    HostPool &P = host_pool();
+    {
+        std::lock_guard<std::mutex> lk(P.m);
+        auto it = P.pinned.find(p);
+        if (it == P.pinned.end()) { free(p); return; }
+        if (P.pooled_bytes + it->second <= kPoolMax) {
+            P.free_blocks.emplace(it->second, p);
+            P.pooled_bytes += it->second;
+            return;
+        }
+        P.pinned.erase(it);
+    }
+    cudaFreeHost(p);
 }

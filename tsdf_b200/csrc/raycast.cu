@@ -266,7 +266,20 @@ distance_bits_kernel(const uint8_t *__restrict__ flags, uint8_t *__restrict__ ou
 #pragma unroll
             for (int w = 0; w < W; w++) planes[p][j][w] = 0ull;
 
+    // A slice past either end of the grid holds no flagged brick and hands back nothing its real neighbours do not reach
+    // by themselves (a path through it is never shorter): its warp only keeps the barriers company.
+    const bool real = z >= 0 && z < nbz;
+    if (!real) {
+#pragma unroll
+        for (int b = 0; b < 2; b++)
+#pragma unroll
+            for (int i = 0; i < R * W; i++) s_bits[b * (32 * kSlice) + warp * kSlice + lane * (R * W) + i] = 0ull;
+    }
     for (int r = 0; r < kDistCap; r++) {
+        if (!real) {
+            if (r < kDistCap - 1) __syncthreads();
+            continue;
+        }
         if (is_out) {
             // m holds D_r: one more for every brick outside it
 #pragma unroll
@@ -1267,7 +1280,10 @@ static int launch_march(RayParams &P, int fastdiv, cudaStream_t s, unsigned int 
         MarchReset reset;
         reset.words = have_words ? reinterpret_cast<unsigned int *>(word) : nullptr;
         reset.n_queue_words = n_queue_words;
-        const bool adaptive = !getenv("TSDF_B200_RAY_CAP") && queue_cap;
+        // (a Z-slab keeps the fixed cap: most rays cross a slab in a few iterations, so even a few thousand set-aside rays
+        // are the longer part — slowest of 8 slabs on frame 10: 298 us with 64, 220 us with 80, 241 us with 96; 263 us before
+        // the continuation moved into the march kernel, tools/slab_march_time.py)
+        const bool adaptive = !getenv("TSDF_B200_RAY_CAP") && queue_cap && !SLAB;
         reset.cap_lo = adaptive ? 64 : P.max_iters; reset.cap_hi = adaptive ? 80 : P.max_iters;
         const double rays = (double)P.width * P.height / (P.tile_stride > 1 ? P.tile_stride : 1);
         reset.thr_lo = (unsigned int)(0.037 * rays); reset.thr_hi = (unsigned int)(0.063 * rays);

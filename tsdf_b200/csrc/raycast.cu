@@ -240,17 +240,20 @@ distance_bits_kernel(const uint8_t *__restrict__ flags, uint8_t *__restrict__ ou
                 const uint8_t *src = flags + ((size_t)z * nby + y) * nbx + w * 64;
                 const int n = min(64, nbx - w * 64);
                 if (nbx % 16 == 0) {
+                    uint32_t half[2] = { 0u, 0u };
                     for (int q = 0; q < n / 16; q++) {
                         const uint4 b = __ldg(reinterpret_cast<const uint4 *>(src) + q);
                         const uint32_t part[4] = { b.x, b.y, b.z, b.w };
 #pragma unroll
                         for (int c = 0; c < 4; c++) {
-                            // one bit per non-zero byte: 0xff per byte, keep the top bits, gather them into a nibble
-                            const uint32_t nz = __vcmpne4(part[c], 0u) & 0x80808080u;
-                            const uint32_t nib = ((nz >> 7) | (nz >> 14) | (nz >> 21) | (nz >> 28)) & 0xfu;
-                            v |= (u64)nib << (16 * q + 4 * c);
+                            // one bit per non-zero byte: 0xff per such byte, its top bit moved to bit 0 of the byte, and the
+                            // four of them gathered into the top nibble by one multiplication (no two partial products
+                            // share a bit position)
+                            const uint32_t nz = (__vcmpne4(part[c], 0u) >> 7) & 0x01010101u;
+                            half[q >> 1] |= ((nz * 0x10204080u) >> 28) << (16 * (q & 1) + 4 * c);
                         }
                     }
+                    v = (u64)half[0] | ((u64)half[1] << 32);
                 } else {
                     for (int x = 0; x < n; x++) v |= (u64)(src[x] != 0) << x;
                 }
@@ -345,13 +348,31 @@ distance_bits_kernel(const uint8_t *__restrict__ flags, uint8_t *__restrict__ ou
     }
     __syncthreads();
     const int n_out = min(kDistOut, nbz - zo0);
-    const int out_bytes = n_out * nby * nbx;
-    for (int i = tid; i < out_bytes; i += blockDim.x) {
-        const int x = i % nbx, row = i / nbx, y = row % nby, o = row / nby;
-        uint32_t v = 0;
+    if (nbx % 8 == 0) {
+        // eight bricks per thread: a byte of each plane is spread into eight bytes holding one bit each (replicate the
+        // byte, keep bit j in byte j, turn "non-zero" into 1 through the carry into bit 7), the planes are summed with
+        // their weights, and the eight distances leave as one 8-byte store
+        const int per_row = nbx / 8, n_chunks = n_out * nby * per_row;
+        for (int i = tid; i < n_chunks; i += blockDim.x) {
+            const int c = i % per_row, row = i / per_row, y = row % nby, o = row / nby;
+            u64 acc = 0;
 #pragma unroll
-        for (int p = 0; p < 5; p++) v |= (uint32_t)((pl[((o * 5 + p) * 32 * R + y) * W + (x >> 6)] >> (x & 63)) & 1ull) << p;
-        out[(size_t)zo0 * nby * nbx + i] = (uint8_t)v;
+            for (int p = 0; p < 5; p++) {
+                const u64 bits = (pl[((o * 5 + p) * 32 * R + y) * W + (c >> 3)] >> (8 * (c & 7))) & 0xffull;
+                const u64 spread = (((bits * 0x0101010101010101ull) & 0x8040201008040201ull) + 0x7f7f7f7f7f7f7f7full) >> 7;
+                acc += (spread & 0x0101010101010101ull) << p;
+            }
+            *reinterpret_cast<u64 *>(out + ((size_t)(zo0 + o) * nby + y) * nbx + 8 * c) = acc;
+        }
+    } else {
+        const int out_bytes = n_out * nby * nbx;
+        for (int i = tid; i < out_bytes; i += blockDim.x) {
+            const int x = i % nbx, row = i / nbx, y = row % nby, o = row / nby;
+            uint32_t v = 0;
+#pragma unroll
+            for (int p = 0; p < 5; p++) v |= (uint32_t)((pl[((o * 5 + p) * 32 * R + y) * W + (x >> 6)] >> (x & 63)) & 1ull) << p;
+            out[(size_t)zo0 * nby * nbx + i] = (uint8_t)v;
+        }
     }
 }
 

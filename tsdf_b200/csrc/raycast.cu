@@ -1384,7 +1384,7 @@ static int launch_march(RayParams &P, int fastdiv, cudaStream_t s, unsigned int 
     else         rc = P.occ ? launch(raycast_kernel<false, true, SLAB>) : launch(raycast_kernel<false, false, SLAB>);
     if (rc) return rc;
     if (want_normals && !P.normals) {
-        // not fused (no room for the counters, image not tile-aligned, pool kernel switched off): the normals kernel, and a copy
+        // not fused (no counters given, no occupancy grid, image not tile-aligned): the normals kernel, and a copy
         rc = tsdf_b200_normals(P.width, P.height, P.vertices, want_normals, s);
         if (rc) return rc;
         if (want_mirror_n)

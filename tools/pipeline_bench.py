@@ -63,6 +63,7 @@ for i in range(args.warmup, total):
 e1.record()
 mesh = eng.extract_mesh()          # first call: table upload, kernel loading
 torch.cuda.synchronize()
+del mesh                           # (the timed call then reuses the block in torch's caching allocator instead of a cudaMalloc)
 e1b = torch.cuda.Event(enable_timing=True)
 e1b.record()
 mesh = eng.extract_mesh()

@@ -152,12 +152,12 @@ class ShardedEngine:
             self.vmap = None
             self._token = torch.zeros(1, dtype=torch.int32, device="cuda")
         self.clear()
-        # kernels per step: 2 pyramid launches (depth staging) + integrate + brick distances (one launch from bit rows, two byte
+        # kernels per step: depth pyramid (one cluster launch) + integrate + brick distances (one launch from bit rows, two byte
         # kernels for grids of 128 x 128 bricks per slice) + march (which finishes its set-aside rays itself) + normals;
         # sharded: + halo integrate + resolve (the barrier is NCCL's)
         wpr, rpl = (self.local_n[0] // BRICK + 63) // 64, (self.local_n[1] // BRICK + 31) // 32
         dist_launches = 1 if (wpr <= 2 and rpl <= 4 and not (wpr == 2 and rpl > 2)) else 2
-        self.launches_per_step = (3 if world == 1 else 5) + dist_launches + (2 if stage_depth else 0)
+        self.launches_per_step = (3 if world == 1 else 5) + dist_launches + (1 if stage_depth else 0)
         if self.layout in ("interleaved", "replica"):
             self.launches_per_step += 2 * (len(self.slabs) - 1)          # one integrate + one halo integrate per owned slab
 

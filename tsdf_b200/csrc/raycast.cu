@@ -1308,6 +1308,10 @@ static int launch_march(RayParams &P, int fastdiv, cudaStream_t s, unsigned int 
         // 2005 with the fixed one).
         const bool thick = !SLAB || (P.cyc_g == 0 && 2u * (P.z_hi - P.z_lo) >= P.nz);
         const bool adaptive = !getenv("TSDF_B200_RAY_CAP") && queue_cap && thick;
+        // A slab thinner than a quarter of the volume that lies in front of a surface holds almost only skimming rays: cap 96
+        // (slowest of 8 slabs on frames 5 / 30 / 54: 212 / 308 / 347 us with 80, 228 / 247 / 247 us with 96; of 4 slabs:
+        // 245 / 253 / 253 against 263 / 273 / 278 us — profiles/r02w_slab_caps.txt)
+        if (SLAB && !getenv("TSDF_B200_RAY_CAP") && P.cyc_g == 0 && 4u * (P.z_hi - P.z_lo) < P.nz && P.max_iters != 0x7fffffff) P.max_iters = 96;
         reset.cap_lo = adaptive ? 64 : P.max_iters; reset.cap_hi = adaptive ? 80 : P.max_iters;
         const double rays = (double)P.width * P.height / (P.tile_stride > 1 ? P.tile_stride : 1);
         reset.thr_lo = (unsigned int)(0.037 * rays); reset.thr_hi = (unsigned int)(0.063 * rays);

@@ -918,14 +918,15 @@ __device__ __noinline__ void continue_entry(const RayParams &P, const float *s_t
     }
 }
 
-// One thread per pixel.  SLAB: the volume arrays hold planes [z_base, z_base + nz_local) of a Z-sharded volume,
-// only samples whose interpolation cell starts in [z_lo, z_hi) are evaluated, and the result is a key.
+// The march without a cap, out of line: for the ray that finds the continuation queue full.
 template <bool FASTDIV, bool SKIP, bool SLAB>
 __device__ __noinline__ void march_ray_cold(const RayParams &P, const float *s_t, const RaySetup &R, int k_first,
                                             int &kh, float &s_hit, uint32_t &samples, RayDebug &dbg) {
     march_ray<FASTDIV, SKIP, SLAB>(P, s_t, R, k_first, TSDF_B200_MAX_SAMPLES - 1, 0x7fffffff, kh, s_hit, samples, dbg);
 }
 
+// One thread per pixel.  SLAB: the volume arrays hold planes [z_base, z_base + nz_local) of a Z-sharded volume,
+// only samples whose interpolation cell starts in [z_lo, z_hi) are evaluated, and the result is a key.
 template <bool FASTDIV, bool SKIP, bool SLAB>
 __global__ void __launch_bounds__(128, TSDF_RAY_MINB)
 raycast_kernel(const __grid_constant__ RayParams P) {
